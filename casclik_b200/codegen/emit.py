@@ -1,0 +1,335 @@
+"""Scalar DAG -> straight-line CUDA (`__device__ __forceinline__`, fp64) + operation counts.
+
+This is the replacement for CasADi's C code generator + shell JIT on the hot path (SURVEY.md
+§2.2): one translation unit per skill that defines `struct Skill` (compile-time sizes, constraint
+table, Jacobian sparsity, `eval` / `eval_qp`) and instantiates the hand-written kernels of
+csrc/clik_pinv.cuh and csrc/clik_qp.cuh on it.  The same emitter can print plain C (used by the
+tests to cross-check the emitted text against the NumPy interpreter with gcc).
+"""
+import math
+
+from ..sym import dag
+from .lower import KIND_EQ, KIND_SET, KIND_VELEQ
+
+# flops per node for the roofline accounting: add/sub/mul/div/sqrt = 1;
+# negation, comparisons, selects = 0; transcendental calls are listed separately.
+_FLOP_OPS = {"add": 1, "sub": 1, "mul": 1, "div": 1, "sqrt": 1}
+_TRANSCENDENTAL = {"sin", "cos", "tan", "asin", "acos", "atan", "atan2", "exp", "log", "pow"}
+
+
+def literal(v: float) -> str:
+    if v != v:
+        return "(0.0/0.0)"
+    if math.isinf(v):
+        return "(1.0/0.0)" if v > 0 else "(-1.0/0.0)"
+    if v == int(v) and abs(v) < 1e15:
+        return "%d.0" % int(v)
+    return float(v).hex()
+
+
+class Emitter(object):
+    """Emits the statements computing a set of nodes, sharing temporaries across calls."""
+
+    def __init__(self, sym_names):
+        self.sym_names = sym_names
+        self.name = {}        # node id -> C expression (temp name, symbol name or literal)
+        self.lines = []
+        self.counter = 0
+        self.hist = {}
+
+    def _ref(self, n):
+        if n.op == "const":
+            return literal(n.val)
+        if n.op == "sym":
+            return self.sym_names[n.id]
+        return self.name[n.id]
+
+    def _tmp(self):
+        self.counter += 1
+        return "v%d" % self.counter
+
+    def require(self, outputs):
+        """Make sure every node in `outputs` has been computed."""
+        pending = [n for n in outputs if n.op not in ("const", "sym") and n.id not in self.name]
+        if not pending:
+            return
+        order = [n for n in dag.topo(pending) if n.op not in ("const", "sym") and n.id not in self.name]
+        # pair sin/cos of the same argument into one sincos call
+        by_arg = {}
+        for n in order:
+            if n.op in ("sin", "cos"):
+                by_arg.setdefault(n.args[0].id, {})[n.op] = n
+        paired = {a: d for a, d in by_arg.items() if len(d) == 2}
+        for n in order:
+            if n.id in self.name:
+                continue
+            self.hist[n.op] = self.hist.get(n.op, 0) + 1
+            a = [self._ref(x) for x in n.args]
+            op = n.op
+            if op in ("sin", "cos") and n.args[0].id in paired:
+                pair = paired[n.args[0].id]
+                s, c = self._tmp(), self._tmp()
+                self.lines.append("double %s, %s; sincos(%s, &%s, &%s);" % (s, c, a[0], s, c))
+                self.name[pair["sin"].id] = s
+                self.name[pair["cos"].id] = c
+                other = pair["cos" if op == "sin" else "sin"]
+                self.hist[other.op] = self.hist.get(other.op, 0) + 1
+                continue
+            if op == "add":
+                rhs = "%s + %s" % (a[0], a[1])
+            elif op == "sub":
+                rhs = "%s - %s" % (a[0], a[1])
+            elif op == "mul":
+                rhs = "%s * %s" % (a[0], a[1])
+            elif op == "div":
+                rhs = "%s / %s" % (a[0], a[1])
+            elif op == "neg":
+                rhs = "-%s" % a[0]
+            elif op in ("sin", "cos", "tan", "asin", "acos", "atan", "exp", "log", "sqrt", "fabs",
+                        "floor", "ceil"):
+                rhs = "%s(%s)" % (op, a[0])
+            elif op in ("atan2", "pow", "fmin", "fmax"):
+                rhs = "%s(%s, %s)" % (op, a[0], a[1])
+            elif op == "sign":
+                rhs = "(double)((%s > 0.0) - (%s < 0.0))" % (a[0], a[0])
+            elif op == "lt":
+                rhs = "(%s < %s) ? 1.0 : 0.0" % (a[0], a[1])
+            elif op == "le":
+                rhs = "(%s <= %s) ? 1.0 : 0.0" % (a[0], a[1])
+            elif op == "eq":
+                rhs = "(%s == %s) ? 1.0 : 0.0" % (a[0], a[1])
+            elif op == "ne":
+                rhs = "(%s != %s) ? 1.0 : 0.0" % (a[0], a[1])
+            elif op == "and":
+                rhs = "(%s != 0.0 && %s != 0.0) ? 1.0 : 0.0" % (a[0], a[1])
+            elif op == "or":
+                rhs = "(%s != 0.0 || %s != 0.0) ? 1.0 : 0.0" % (a[0], a[1])
+            elif op == "not":
+                rhs = "(%s == 0.0) ? 1.0 : 0.0" % a[0]
+            elif op == "if_else":
+                rhs = "(%s != 0.0) ? %s : %s" % (a[0], a[1], a[2])
+            else:  # pragma: no cover
+                raise NotImplementedError(op)
+            t = self._tmp()
+            self.lines.append("const double %s = %s;" % (t, rhs))
+            self.name[n.id] = t
+
+    def assign(self, lhs, node):
+        self.require([node])
+        self.lines.append("%s = %s;" % (lhs, self._ref(node)))
+
+    def counts(self):
+        flops = sum(_FLOP_OPS.get(op, 0) * k for op, k in self.hist.items())
+        trans = {op: k for op, k in self.hist.items() if op in _TRANSCENDENTAL}
+        return {"flops": flops, "transcendentals": trans, "ops": dict(self.hist)}
+
+
+# ----------------------------------------------------------------------------------------------
+# hand-written-kernel flop model (mode 0 of the static path), mirrors csrc/clik_pinv.cuh
+# ----------------------------------------------------------------------------------------------
+
+def _spd_solve_flops(k):
+    f = 0
+    for j in range(k):
+        f += 2 * j + 2                      # diagonal fma chain + rsqrt (sqrt + div)
+        f += (k - j - 1) * (2 * j + 1)      # column below the diagonal
+    f += 2 * sum(2 * i + 1 for i in range(k))   # forward + backward substitution
+    return f
+
+
+def pinv_mode0_flops(prog):
+    """Arithmetic of the accepted-mode-0 path in clik_pinv.cuh for this skill (fma = 2)."""
+    ns = prog.ns
+    nz = {}
+    for b in prog.blocks:
+        for r in range(b["rows"]):
+            nz[b["row0"] + r] = [n is not dag.ZERO for n in b["J"][r]]
+
+    def dot_rows(ra, rb):
+        c = sum(1 for j in range(ns) if nz[ra][j] and nz[rb][j])
+        return max(2 * c - 1, 0)
+
+    def pinv_times(rows):
+        k = len(rows)
+        wide = (ns >= k) if prog.damped else (k < ns)
+        f = 0
+        if wide:
+            for a in range(k):
+                for c in range(a + 1):
+                    f += dot_rows(rows[a], rows[c]) + (1 if a == c else 0)
+            f += _spd_solve_flops(k)
+            for j in range(ns):
+                f += max(2 * sum(1 for a in rows if nz[a][j]) - 1, 0)
+        else:
+            for i in range(ns):
+                for c in range(i + 1):
+                    f += max(2 * sum(1 for a in rows if nz[a][i] and nz[a][c]) - 1, 0) + (1 if i == c else 0)
+            for j in range(ns):
+                f += max(2 * sum(1 for a in rows if nz[a][j]) - 1, 0)
+            f += _spd_solve_flops(ns)
+        return f
+
+    def nullspace(rows):
+        f = sum(max(2 * sum(nz[a]) - 1, 0) for a in rows)
+        return f + pinv_times(rows) + ns
+
+    flops = 0
+    stack = []
+    for b in prog.blocks:
+        own = list(range(b["row0"], b["row0"] + b["rows"]))
+        if b["kind"] in (KIND_EQ, KIND_VELEQ):
+            flops += pinv_times(own)
+            if not stack:
+                flops += ns
+                stack = stack + own
+                if b["kind"] == KIND_EQ:
+                    flops += nullspace(stack) + ns
+                    stack = stack + own
+            else:
+                flops += nullspace(stack) + ns
+                stack = stack + own
+        elif b["kind"] == KIND_SET:
+            flops += 2 * sum(nz[b["row0"]]) + 4     # in-tangent-cone test of the inactive set
+    return flops
+
+
+# ----------------------------------------------------------------------------------------------
+# translation unit
+# ----------------------------------------------------------------------------------------------
+
+def _switch(name, values, ret="int"):
+    body = " ".join("case %d: return %s;" % (i, v) for i, v in enumerate(values))
+    return ("  __host__ __device__ static constexpr %s %s(int c) { switch (c) { %s default: return 0; } }"
+            % (ret, name, body))
+
+
+def emit_skill(pinv=None, qp=None, label="skill", block_threads=128, min_blocks=0):
+    """-> (source text, meta dict).  `pinv`: PinvProgram or None, `qp`: QpProgram or None."""
+    ref = pinv if pinv is not None else qp
+    if ref is None:
+        raise ValueError("nothing to emit")
+    nq, nxv, ny = ref.n_rob, ref.n_virt, ref.n_in
+    meta = {"label": label, "n_robot": nq, "n_virtual": nxv, "n_input": ny,
+            "has_pinv": pinv is not None, "has_qp": qp is not None,
+            "n_modes": 1, "qp_n": 0, "qp_m": 0, "block_threads": block_threads}
+    out = []
+    out.append("// generated by casclik_b200.codegen for skill %r -- do not edit" % label)
+    out.append('#include "clik_pinv.cuh"')
+    out.append('#include "clik_qp.cuh"')
+    out.append("")
+    pre_struct = []
+    struct_at = len(out)
+    out.append("struct Skill {")
+    out.append("  static constexpr int NQ = %d, NX = %d, NY = %d, NS = %d;" % (nq, nxv, ny, nq + nxv))
+    sig = ("const double t, const double (&q)[%d], const double (&x)[%d], const double (&y)[%d]"
+           % (max(nq, 1), max(nxv, 1), max(ny, 1)))
+
+    if pinv is not None:
+        from ..controllers._modes import activation_map
+        amap = activation_map(pinv.n_sets)
+        masks = [sum(b << k for k, b in enumerate(row)) for row in amap] or [0]
+        meta["n_modes"] = len(masks)
+        kinds = [b["kind"] for b in pinv.blocks]
+        out.append("  static constexpr int NC = %d, M = %d, NSETS = %d, NMODES = %d, MAXROWS = %d;"
+                   % (len(pinv.blocks), pinv.m, pinv.n_sets, len(masks), pinv.max_rows))
+        out.append("  static constexpr bool DAMPED = %s;" % ("true" if pinv.damped else "false"))
+        out.append("  static constexpr double LAMBDA = %s;" % literal(pinv.damping))
+        out.append(_switch("kind", kinds))
+        out.append(_switch("row0", [b["row0"] for b in pinv.blocks]))
+        out.append(_switch("rows", [b["rows"] for b in pinv.blocks]))
+        out.append(_switch("set_index", [max(b["set_index"], 0) for b in pinv.blocks]))
+        rowmask = []
+        for b in pinv.blocks:
+            for r in range(b["rows"]):
+                rowmask.append(sum((1 << j) for j, n in enumerate(b["J"][r]) if n is not dag.ZERO))
+        if pinv.ns > 63:
+            raise NotImplementedError("more than 63 state variables")
+        out.append("  __host__ __device__ static constexpr bool jnz(int r, int j) {")
+        out.append("    constexpr unsigned long long m[%d] = {%s};" % (
+            len(rowmask), ", ".join("0x%xULL" % v for v in rowmask)))
+        out.append("    return (m[r] >> j) & 1ULL;")
+        out.append("  }")
+        if len(masks) > 4096:
+            raise NotImplementedError("more than 12 SetConstraints (4096 modes)")
+        pre_struct.append("__device__ const unsigned short clik_mode_tab[%d] = {%s};" % (
+            len(masks), ", ".join(str(v) for v in masks)))
+        out.append("  __device__ static __forceinline__ unsigned mode_mask(int mi) { return clik_mode_tab[mi]; }")
+        em = Emitter(pinv.syms.names)
+        body = []
+        for b in pinv.blocks:
+            for r in range(b["rows"]):
+                gr = b["row0"] + r
+                for j in range(pinv.ns):
+                    em.assign("d.J[%d]" % (gr * pinv.ns + j), b["J"][r][j])
+                if b["kind"] in (KIND_EQ, KIND_VELEQ):
+                    em.assign("d.des[%d]" % gr, b["des"][r])
+                elif b["kind"] == KIND_SET:
+                    em.assign("d.e[%d]" % gr, b["e"][r])
+                    em.assign("d.jt[%d]" % gr, b["jt"][r])
+                    em.assign("d.smin[%d]" % gr, b["smin"][r])
+                    em.assign("d.smax[%d]" % gr, b["smax"][r])
+        body = em.lines
+        out.append("  __device__ static __forceinline__ void eval(%s, clik::PinvData<Skill>& d) {" % sig)
+        out += ["    " + ln for ln in body]
+        out.append("  }")
+        cnt = em.counts()
+        meta["pinv_eval"] = cnt
+        meta["pinv_algebra_flops_mode0"] = pinv_mode0_flops(pinv)
+        meta["pinv_flops_mode0"] = cnt["flops"] + meta["pinv_algebra_flops_mode0"]
+        meta["pinv_bytes_per_step"] = 8 * (1 + nq + nxv + ny) + 8 * (nq + nxv) + 4
+        meta["jacobian_nnz"] = sum(bin(v).count("1") for v in rowmask)
+        meta["rows"] = pinv.m
+
+    if qp is not None:
+        meta["qp_n"], meta["qp_m"] = qp.nx, qp.m
+        out.append("  static constexpr int QN = %d, QM = %d;" % (qp.nx, qp.m))
+        em = Emitter(qp.syms.names)
+        for r in range(qp.m):
+            for j in range(qp.nx):
+                em.assign("d.A[%d]" % (r * qp.nx + j), qp.A[r][j])
+            em.assign("d.lb[%d]" % r, qp.lb[r])
+            em.assign("d.ub[%d]" % r, qp.ub[r])
+        for j in range(qp.nx):
+            em.assign("d.h[%d]" % j, qp.h[j])
+        out.append("  __device__ static __forceinline__ void eval_qp(%s, clik::QpData<Skill>& d) {" % sig)
+        out += ["    " + ln for ln in em.lines]
+        out.append("  }")
+        meta["qp_eval"] = em.counts()
+        meta["qp_bytes_per_step"] = 8 * (1 + nq + nxv + ny) + 8 * qp.nx + 4 + 8
+
+    out.append("};")
+    out.append("")
+    out[struct_at:struct_at] = pre_struct
+    bounds = "__launch_bounds__(%d%s)" % (block_threads, (", %d" % min_blocks) if min_blocks else "")
+    if pinv is not None:
+        out.append('extern "C" __global__ void %s clik_pinv_kernel(' % bounds)
+        out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
+        out.append("    const double* y, double* qdot, double* xdot, int* mode) {")
+        out.append("  clik::pinv_step<Skill>(N, t, t_stride, q, x, y, qdot, xdot, mode);")
+        out.append("}")
+    if qp is not None:
+        out.append('extern "C" __global__ void __launch_bounds__(%d) clik_qp_kernel(' % block_threads)
+        out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
+        out.append("    const double* y, const double* x0, double* sol, int* status, unsigned* active,")
+        out.append("    int max_iter) {")
+        out.append("  clik::qp_step<Skill>(N, t, t_stride, q, x, y, x0, sol, status, active, max_iter);")
+        out.append("}")
+    out.append('extern "C" __global__ void clik_sizes_kernel(int* o) {')
+    out.append("  o[0] = %d; o[1] = %d; o[2] = %d; o[3] = %d; o[4] = %d; o[5] = %d; o[6] = 0; o[7] = 0;"
+               % (nq, nxv, ny, meta["n_modes"], meta["qp_n"], meta["qp_m"]))
+    out.append("}")
+    return "\n".join(out) + "\n", meta
+
+
+def emit_c_function(name, sym_names, outputs, arg_decl):
+    """Plain C version of a node list (tests: gcc-compiled text vs NumPy interpreter)."""
+    em = Emitter(sym_names)
+    for i, n in enumerate(outputs):
+        em.assign("out[%d]" % i, n)
+    lines = ["#include <math.h>",
+             "static void sincos_(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }",
+             "#define sincos sincos_",
+             "void %s(%s, double* out) {" % (name, arg_decl)]
+    lines += ["  " + ln for ln in em.lines]
+    lines.append("}")
+    return "\n".join(lines) + "\n"

@@ -1,0 +1,192 @@
+"""PseudoInverseController — set-based singularity-robust multiple-task-priority controller,
+evaluated on the GPU for one or N instances.
+
+Drop-in for reference casclik/controllers/pseudo_inverse.py: same constructor, option keys and
+defaults (:42-66), `setup_problem_functions` / `setup_solver` / `setup_initial_problem_solver` /
+`solve_initial_problem` / `solve` signatures and return conventions (:453-556), and the same
+public attributes (`current_mode`, `modes`, `activation_map`, `n_modes`, `n_set_constraints`,
+`state_var`, `n_state_var`).  Instead of one JIT-compiled CasADi function per mode, setup emits
+one CUDA translation unit for the skill (casclik_b200/codegen) and loads it through the C ABI
+(include/clik.h); `solve` runs a batch of one, `solve_batch` runs N.
+
+Options are read when `setup_*` runs, not at construction, because the reference stores the dict
+by reference and the notebooks mutate it in between.
+"""
+import numpy as np
+
+from .. import build, runtime
+from .. import sym as cs
+from ..codegen import PinvProgram, emit_skill
+from ..constraints import SetConstraint
+from ._modes import activation_map
+from .base_controller import BaseController, Batch, as_vector, dm_column
+
+
+class PseudoInverseController(BaseController):
+    """Pseudo inverse controller.
+
+    Args:
+        skill_spec (SkillSpecification): skill specification
+        options (dict): feedforward (True), multidim_sets (False),
+            converge_final_set_to_max (False), pinv_method ("damped" | "standard"),
+            damping_factor (1e-7), function_opts (kept for compatibility; the CUDA build ignores it)
+    """
+    controller_type = "PseudoInverseController"
+    options_info = """feedforward, multidim_sets, converge_final_set_to_max, pinv_method,
+    damping_factor, function_opts"""
+
+    def __init__(self, skill_spec, options=None):
+        self.current_mode = None
+        self._compiled = None
+        self.skill_spec = skill_spec
+        self.options = options
+
+    # ---- options / skill -----------------------------------------------------------------------
+    @property
+    def options(self):
+        return self._options
+
+    @options.setter
+    def options(self, opt):
+        if opt is None:
+            opt = {}
+        opt.setdefault("feedforward", True)
+        opt.setdefault("multidim_sets", False)
+        opt.setdefault("converge_final_set_to_max", False)
+        opt.setdefault("pinv_method", "damped")   # "standard" | "damped"
+        opt.setdefault("damping_factor", 1e-7)
+        fopts = opt.setdefault("function_opts", {})
+        fopts.setdefault("jit", True)
+        fopts.setdefault("print_time", False)
+        fopts.setdefault("jit_options", {"flags": "-O2"})
+        self._options = opt
+
+    @property
+    def skill_spec(self):
+        return self._skill_spec
+
+    @skill_spec.setter
+    def skill_spec(self, spec):
+        counts = spec.count_constraints()
+        self.n_set_constraints = counts["set"]
+        self.n_modes = 2 ** counts["set"]
+        state = [spec.robot_var]
+        cntrl = [spec.robot_vel_var]
+        n_state = spec.n_robot_var
+        if spec.virtual_var is not None:
+            state.append(spec.virtual_var)
+            cntrl.append(spec.virtual_vel_var)
+            n_state += spec.n_virtual_var
+        self.state_var = cs.vertcat(*state)
+        self.cntrl_var = cntrl
+        self.n_state_var = n_state
+        self._skill_spec = spec
+        self._compiled = None
+        self.create_activation_map()
+
+    def create_activation_map(self):
+        self.activation_map = activation_map(self.n_set_constraints)
+
+    # ---- setup ------------------------------------------------------------------------------------
+    def get_problem_expressions(self):
+        """Mode table.  The reference stores a CasADi expression per mode here; this engine keeps
+        the per-mode algebra inside one kernel, so a mode entry only lists which sets it
+        activates."""
+        sets = [c for c in self.skill_spec.constraints if isinstance(c, SetConstraint)]
+        rows = self.activation_map or [[]]
+        self.modes = [{"activation": list(bits),
+                       "active_set_names": [c.label for c, b in zip(sets, bits) if b],
+                       "inactive_set_names": [c.label for c, b in zip(sets, bits) if not b]}
+                      for bits in rows]
+        return self.modes
+
+    def setup_problem_functions(self, load=True):
+        """Lower the skill, emit CUDA, compile for sm_100a (cached) and load the cubin.
+        `load=False` stops after compilation (usable without a GPU)."""
+        self.get_problem_expressions()
+        prog = PinvProgram(self.skill_spec, self.options)
+        source, meta = emit_skill(pinv=prog, label=self.skill_spec.label)
+        cubin, path = build.compile_cubin(source, tag="pinv_" + self.skill_spec.label)
+        self.kernel_source, self.kernel_meta, self.cubin_path = source, meta, path
+        self._nx, self._ny = prog.n_virt, prog.n_in
+        self._cubin = cubin
+        self._compiled = None
+        if load:
+            self._compiled = runtime.CompiledSkill(cubin, meta, n_slack=self.skill_spec.n_slack_var)
+
+    def setup_initial_problem_solver(self):
+        """Nothing to set up (same as the reference, pseudo_inverse.py:485-488)."""
+        pass
+
+    def solve_initial_problem(self, time_var0, robot_var0, virtual_var0=None,
+                              robot_vel_var0=None, input_var0=None):
+        """Zeros, like the reference (pseudo_inverse.py:490-504)."""
+        spec = self.skill_spec
+        res_virt = cs.DM.zeros(spec.virtual_var.size()) if virtual_var0 is not None else None
+        res_slack = cs.DM.zeros(spec.slack_var.size()) if spec.slack_var is not None else None
+        return res_virt, res_slack
+
+    def setup_solver(self):
+        self.setup_problem_functions()
+
+    def _skill(self):
+        if self._compiled is None:
+            if getattr(self, "_cubin", None) is None:
+                raise RuntimeError("call setup_problem_functions() / setup_solver() before solve()")
+            self._compiled = runtime.CompiledSkill(self._cubin, self.kernel_meta,
+                                                   n_slack=self.skill_spec.n_slack_var)
+        return self._compiled
+
+    # ---- step --------------------------------------------------------------------------------------
+    def solve_batch(self, time_var, robot_var, virtual_var=None, input_var=None, out=None):
+        """Controller step for N instances.
+
+        robot_var (n_robot, N), virtual_var (n_virtual, N), input_var (n_input, N): float64,
+        coordinate-major; torch CUDA tensors (zero-copy, asynchronous on the current stream) or
+        NumPy arrays (pipelined host path).  time_var: float or (N,).
+        Returns (robot_vel (n_robot, N), virtual_vel (n_virtual, N) | None, mode (N,) int32) with
+        mode = index into `activation_map` (0 when the skill has no sets), -1 = no admissible
+        mode (velocities are zero)."""
+        skill = self._skill()
+        spec = self.skill_spec
+        nq, nx, ny = spec.n_robot_var, self._nx, self._ny
+        b = Batch(nq, nx, ny, time_var, robot_var, virtual_var, input_var if ny else None)
+        if out is None:
+            qdot = b.empty(nq)
+            xdot = b.empty(nx) if nx else None
+            mode = b.empty(0, "i32")
+        else:
+            qdot, xdot, mode = out
+        lib = runtime.load_library()
+        if b.on_device:
+            runtime.check(lib.clik_pinv_step(skill.handle, b.N, b.tp, b.t_stride, b.qp, b.xp, b.yp,
+                                             b.ptr(qdot), b.ptr(xdot), b.ptr(mode), b.stream()))
+        else:
+            runtime.check(lib.clik_pinv_step_host(skill.handle, b.N, b.tp, b.t_stride, b.qp, b.xp,
+                                                  b.yp, b.ptr(qdot), b.ptr(xdot), b.ptr(mode)))
+        return qdot, xdot, mode
+
+    def solve(self, time_var, robot_var, virtual_var=None, input_var=None,
+              warmstart_robot_vel_var=None, warmstart_virtual_vel_var=None,
+              warmstart_slack_var=None):
+        """One controller step -> (cntrl_rob, cntrl_virt | None, None); sets `current_mode`."""
+        spec = self.skill_spec
+        nq = spec.n_robot_var
+        q = as_vector(robot_var, nq, "robot_var").reshape(nq, 1)
+        use_virt = virtual_var is not None and spec._has_virtual
+        x = None
+        if self._nx:
+            if spec._has_virtual and virtual_var is None:
+                raise ValueError("the skill depends on virtual_var: a value is required")
+            x = (as_vector(virtual_var, self._nx, "virtual_var") if virtual_var is not None
+                 else np.zeros(self._nx)).reshape(self._nx, 1)
+        y = None
+        if self._ny:
+            if input_var is None:
+                raise ValueError("the skill depends on input_var: a value is required")
+            y = as_vector(input_var, self._ny, "input_var").reshape(self._ny, 1)
+        t = np.array([float(time_var)])
+        qdot, xdot, mode = self.solve_batch(t, q, x, y)
+        self.current_mode = int(mode[0])
+        cntrl_virt = dm_column(xdot[:, 0]) if use_virt else None
+        return dm_column(qdot[:, 0]), cntrl_virt, None

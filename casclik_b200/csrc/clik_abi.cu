@@ -1,0 +1,464 @@
+// clik_abi.cu — host side of the C ABI declared in include/clik.h (libclik_b200.so).
+//
+// Loads the per-skill sm_100a cubin emitted by casclik_b200/codegen (CUDA runtime library API:
+// cudaLibraryLoadData / cudaLibraryGetKernel), picks a persistent grid (SM count x resident CTAs),
+// and launches the fused controller-step kernels.  No torch types, no Python; the static CUDA
+// runtime loads libcuda lazily, so the library itself loads on a machine without a GPU and only
+// the entry points that touch a device fail (CLIK_ERR_NOGPU / CLIK_ERR_CUDA).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/clik.h"
+#include "clik_qp.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+clik_status fail(clik_status code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? CLIK_ERR_NOGPU \
+                                                                               : CLIK_ERR_CUDA, \
+                  "%s failed: %s", #call, cudaGetErrorString(e_));                            \
+  } while (0)
+
+struct KernelInfo {
+  cudaKernel_t kernel = nullptr;
+  int grid = 0, block = 0, regs = 0, local_bytes = 0;
+};
+
+// device scratch for the host-buffer pipeline (two slots, sized on demand)
+struct Scratch {
+  void* dev[2] = {nullptr, nullptr};
+  size_t bytes[2] = {0, 0};
+  cudaStream_t stream[2] = {nullptr, nullptr};
+};
+
+}  // namespace
+
+struct clik_skill {
+  clik_skill_desc desc;
+  cudaLibrary_t lib = nullptr;
+  KernelInfo pinv, qp;
+  int sm_count = 0;
+  std::mutex mu;  // guards scratch
+  Scratch scratch;
+};
+
+namespace {
+
+clik_status setup_kernel(clik_skill* s, const char* name, KernelInfo* k) {
+  cudaError_t e = cudaLibraryGetKernel(&k->kernel, s->lib, name);
+  if (e != cudaSuccess)
+    return fail(CLIK_ERR_IMAGE, "cubin has no kernel %s: %s", name, cudaGetErrorString(e));
+  cudaFuncAttributes attr;
+  CK(cudaFuncGetAttributes(&attr, (const void*)k->kernel));
+  k->regs = attr.numRegs;
+  k->local_bytes = (int)attr.localSizeBytes;
+  k->block = s->desc.block_threads > 0 ? s->desc.block_threads : 128;
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k->kernel, k->block, 0));
+  if (per_sm < 1) per_sm = 1;
+  k->grid = s->sm_count * per_sm;
+  return CLIK_OK;
+}
+
+int grid_for(const KernelInfo& k, int64_t N) {
+  int64_t need = (N + k.block - 1) / k.block;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(need, k.grid));
+}
+
+clik_status check_common(const clik_skill* s, int64_t N, const double* t, const double* q,
+                         const double* x, const double* y) {
+  if (!s) return fail(CLIK_ERR_INVALID, "skill is NULL");
+  if (N < 0) return fail(CLIK_ERR_INVALID, "N < 0");
+  if (N == 0) return CLIK_OK;
+  if (!t || !q) return fail(CLIK_ERR_INVALID, "t and q are required");
+  if (s->desc.n_virtual > 0 && !x) return fail(CLIK_ERR_INVALID, "skill has virtual_var: x is required");
+  if (s->desc.n_input > 0 && !y) return fail(CLIK_ERR_INVALID, "skill reads input_var: y is required");
+  return CLIK_OK;
+}
+
+// ---- dense QP kernel (the cs.conic call for numeric H/A/lb/ub) --------------------------------------
+constexpr int DENSE_NX = 16, DENSE_M = 32;
+
+__global__ void clik_qp_dense_kernel(long long N, int nx, int m, const double* __restrict__ h,
+                                     const double* __restrict__ A, const double* __restrict__ lb,
+                                     const double* __restrict__ ub, const double* __restrict__ x0,
+                                     double* __restrict__ sol, int* __restrict__ status,
+                                     unsigned* __restrict__ active, int max_iter) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    double Al[DENSE_M * DENSE_NX], lbl[DENSE_M], ubl[DENSE_M], hl[DENSE_NX], xs[DENSE_NX], x0l[DENSE_NX];
+    for (int j = 0; j < nx; ++j) hl[j] = h[(long long)j * N + i];
+    for (int r = 0; r < m; ++r) {
+      lbl[r] = lb[(long long)r * N + i];
+      ubl[r] = ub[(long long)r * N + i];
+      for (int j = 0; j < nx; ++j) Al[r * nx + j] = A[(long long)(r * nx + j) * N + i];
+    }
+    if (x0) for (int j = 0; j < nx; ++j) x0l[j] = x0[(long long)j * N + i];
+    unsigned mu, ml;
+    int st = clik::qp_dual_active_set<DENSE_NX, DENSE_M>(nx, m, Al, lbl, ubl, hl, x0 ? x0l : nullptr,
+                                                         xs, &mu, &ml, max_iter);
+    for (int j = 0; j < nx; ++j) sol[(long long)j * N + i] = xs[j];
+    if (status) status[i] = st;
+    if (active) { active[i] = mu; active[N + i] = ml; }
+  }
+}
+
+// ---- measurement helpers -------------------------------------------------------------------------------
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+  // 8 independent dependent-chains per thread: enough ILP to saturate the fp64 pipe
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+__global__ void fill_kernel(double* p, size_t n, double v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+std::mutex g_flush_mu;
+double* g_flush_buf[64] = {nullptr};
+constexpr size_t FLUSH_BYTES = (size_t)256 << 20;  // 256 MiB > 126 MB L2
+
+// ---- host-buffer pipeline ----------------------------------------------------------------------------
+struct Field {
+  const void* src;   // host source (input) or nullptr
+  void* dst;         // host destination (output) or nullptr
+  int rows;          // SoA rows
+  int elem;          // bytes per element
+  int stride;        // 1 = per instance, 0 = broadcast scalar row (only for t)
+  size_t dev_off;    // byte offset inside the slot buffer
+};
+
+clik_status ensure_scratch(clik_skill* s, int slot, size_t bytes) {
+  Scratch& sc = s->scratch;
+  if (!sc.stream[slot]) CK(cudaStreamCreateWithFlags(&sc.stream[slot], cudaStreamNonBlocking));
+  if (sc.bytes[slot] < bytes) {
+    if (sc.dev[slot]) CK(cudaFree(sc.dev[slot]));
+    sc.dev[slot] = nullptr;
+    sc.bytes[slot] = 0;
+    CK(cudaMalloc(&sc.dev[slot], bytes));
+    sc.bytes[slot] = bytes;
+  }
+  return CLIK_OK;
+}
+
+constexpr int64_t HOST_CHUNK = 1 << 19;
+
+template <class Launch>
+clik_status run_host_pipeline(clik_skill* s, int64_t N, std::vector<Field>& f, Launch launch) {
+  std::lock_guard<std::mutex> lock(s->mu);
+  CK(cudaSetDevice(s->desc.device));
+  const int64_t chunk = std::min<int64_t>(N, HOST_CHUNK);
+  size_t bytes = 0;
+  for (auto& fl : f) {
+    fl.dev_off = bytes;
+    bytes += (((size_t)fl.rows * chunk * fl.elem) + 255) & ~(size_t)255;
+  }
+  for (int slot = 0; slot < 2; ++slot) {
+    clik_status st = ensure_scratch(s, slot, bytes);
+    if (st != CLIK_OK) return st;
+  }
+  int slot = 0;
+  for (int64_t i0 = 0; i0 < N; i0 += chunk, slot ^= 1) {
+    const int64_t c = std::min<int64_t>(chunk, N - i0);
+    cudaStream_t st = s->scratch.stream[slot];
+    char* base = (char*)s->scratch.dev[slot];
+    for (auto& fl : f) {
+      if (!fl.src) continue;
+      if (fl.stride == 0) {
+        CK(cudaMemcpyAsync(base + fl.dev_off, fl.src, fl.elem, cudaMemcpyHostToDevice, st));
+      } else {
+        CK(cudaMemcpy2DAsync(base + fl.dev_off, (size_t)c * fl.elem,
+                             (const char*)fl.src + (size_t)i0 * fl.elem, (size_t)N * fl.elem,
+                             (size_t)c * fl.elem, fl.rows, cudaMemcpyHostToDevice, st));
+      }
+    }
+    clik_status ls = launch(base, c, st);
+    if (ls != CLIK_OK) return ls;
+    for (auto& fl : f) {
+      if (!fl.dst) continue;
+      CK(cudaMemcpy2DAsync((char*)fl.dst + (size_t)i0 * fl.elem, (size_t)N * fl.elem,
+                           base + fl.dev_off, (size_t)c * fl.elem, (size_t)c * fl.elem, fl.rows,
+                           cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CK(cudaStreamSynchronize(s->scratch.stream[0]));
+  CK(cudaStreamSynchronize(s->scratch.stream[1]));
+  return CLIK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* clik_last_error(void) { return g_err.c_str(); }
+int32_t clik_abi_version(void) { return CLIK_ABI_VERSION; }
+
+int32_t clik_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc* desc,
+                            clik_skill** out) {
+  if (!cubin || len == 0 || !desc || !out) return fail(CLIK_ERR_INVALID, "NULL argument");
+  if (desc->abi_version != CLIK_ABI_VERSION)
+    return fail(CLIK_ERR_INVALID, "descriptor ABI version %d != library %d", desc->abi_version,
+                CLIK_ABI_VERSION);
+  if (desc->n_robot <= 0) return fail(CLIK_ERR_INVALID, "n_robot must be positive");
+  *out = nullptr;
+  CK(cudaSetDevice(desc->device));
+  clik_skill* s = new clik_skill();
+  s->desc = *desc;
+  cudaError_t e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, desc->device);
+  if (e == cudaSuccess) e = cudaLibraryLoadData(&s->lib, cubin, nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (e != cudaSuccess) {
+    delete s;
+    return fail(CLIK_ERR_IMAGE, "cannot load cubin (%zu bytes): %s", len, cudaGetErrorString(e));
+  }
+  clik_status st = CLIK_OK;
+  if (desc->has_pinv) st = setup_kernel(s, "clik_pinv_kernel", &s->pinv);
+  if (st == CLIK_OK && desc->has_qp) st = setup_kernel(s, "clik_qp_kernel", &s->qp);
+  // the image carries its own sizes: refuse a descriptor that disagrees
+  if (st == CLIK_OK) {
+    cudaKernel_t probe;
+    if (cudaLibraryGetKernel(&probe, s->lib, "clik_sizes_kernel") == cudaSuccess) {
+      int* dsz = nullptr;
+      int hsz[8] = {0};
+      if (cudaMalloc(&dsz, sizeof(hsz)) == cudaSuccess) {
+        void* args[] = {&dsz};
+        cudaError_t le = cudaLaunchKernel((const void*)probe, dim3(1), dim3(1), args, 0, nullptr);
+        if (le == cudaSuccess) le = cudaMemcpy(hsz, dsz, sizeof(hsz), cudaMemcpyDeviceToHost);
+        cudaFree(dsz);
+        if (le != cudaSuccess) {
+          st = fail(CLIK_ERR_CUDA, "size probe failed: %s", cudaGetErrorString(le));
+        } else if (hsz[0] != desc->n_robot || hsz[1] != desc->n_virtual || hsz[2] != desc->n_input ||
+                   hsz[3] != desc->n_modes || hsz[4] != desc->qp_n || hsz[5] != desc->qp_m) {
+          st = fail(CLIK_ERR_IMAGE,
+                    "descriptor does not match cubin: image (n_robot %d, n_virtual %d, n_input %d, "
+                    "n_modes %d, qp %dx%d)",
+                    hsz[0], hsz[1], hsz[2], hsz[3], hsz[5], hsz[4]);
+        }
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
+  if (st != CLIK_OK) {
+    cudaLibraryUnload(s->lib);
+    delete s;
+    return st;
+  }
+  *out = s;
+  return CLIK_OK;
+}
+
+void clik_skill_free(clik_skill* s) {
+  if (!s) return;
+  cudaSetDevice(s->desc.device);
+  for (int i = 0; i < 2; ++i) {
+    if (s->scratch.dev[i]) cudaFree(s->scratch.dev[i]);
+    if (s->scratch.stream[i]) cudaStreamDestroy(s->scratch.stream[i]);
+  }
+  if (s->lib) cudaLibraryUnload(s->lib);
+  delete s;
+}
+
+clik_status clik_skill_launch_info(const clik_skill* s, int32_t which, int32_t* grid, int32_t* block,
+                                   int32_t* regs, int32_t* local_bytes) {
+  if (!s) return fail(CLIK_ERR_INVALID, "skill is NULL");
+  const KernelInfo& k = which == 0 ? s->pinv : s->qp;
+  if (!k.kernel) return fail(CLIK_ERR_INVALID, "skill has no such kernel");
+  if (grid) *grid = k.grid;
+  if (block) *block = k.block;
+  if (regs) *regs = k.regs;
+  if (local_bytes) *local_bytes = k.local_bytes;
+  return CLIK_OK;
+}
+
+clik_status clik_pinv_step(const clik_skill* s, int64_t N, const double* t, int32_t t_stride,
+                           const double* q, const double* x, const double* y, double* qdot,
+                           double* xdot, int32_t* mode, void* stream) {
+  clik_status st = check_common(s, N, t, q, x, y);
+  if (st != CLIK_OK || N == 0) return st;
+  if (!s->pinv.kernel) return fail(CLIK_ERR_INVALID, "skill was built without the pinv kernel");
+  if (!qdot) return fail(CLIK_ERR_INVALID, "qdot is required");
+  if (s->desc.n_virtual > 0 && !xdot) return fail(CLIK_ERR_INVALID, "xdot is required");
+  CK(cudaSetDevice(s->desc.device));
+  long long n = N;
+  int ts = t_stride ? 1 : 0;
+  void* args[] = {&n, &t, &ts, &q, &x, &y, &qdot, &xdot, &mode};
+  CK(cudaLaunchKernel((const void*)s->pinv.kernel, dim3(grid_for(s->pinv, N)), dim3(s->pinv.block),
+                      args, 0, (cudaStream_t)stream));
+  return CLIK_OK;
+}
+
+clik_status clik_qp_step(const clik_skill* s, int64_t N, const double* t, int32_t t_stride,
+                         const double* q, const double* x, const double* y, const double* x0,
+                         double* sol, int32_t* status, uint32_t* active, int32_t max_iter,
+                         void* stream) {
+  clik_status st = check_common(s, N, t, q, x, y);
+  if (st != CLIK_OK || N == 0) return st;
+  if (!s->qp.kernel) return fail(CLIK_ERR_INVALID, "skill was built without the QP kernel");
+  if (!sol) return fail(CLIK_ERR_INVALID, "sol is required");
+  CK(cudaSetDevice(s->desc.device));
+  long long n = N;
+  int ts = t_stride ? 1 : 0;
+  int mi = max_iter > 0 ? max_iter : 10 * (s->desc.qp_n + s->desc.qp_m);
+  void* args[] = {&n, &t, &ts, &q, &x, &y, &x0, &sol, &status, &active, &mi};
+  CK(cudaLaunchKernel((const void*)s->qp.kernel, dim3(grid_for(s->qp, N)), dim3(s->qp.block), args,
+                      0, (cudaStream_t)stream));
+  return CLIK_OK;
+}
+
+clik_status clik_qp_dense(int32_t device, int64_t N, int32_t nx, int32_t m, const double* h,
+                          const double* A, const double* lb, const double* ub, const double* x0,
+                          double* sol, int32_t* status, uint32_t* active, int32_t max_iter,
+                          void* stream) {
+  if (N < 0 || nx <= 0 || m < 0) return fail(CLIK_ERR_INVALID, "bad sizes");
+  if (nx > DENSE_NX || m > DENSE_M)
+    return fail(CLIK_ERR_INVALID, "clik_qp_dense supports nx <= %d, m <= %d", DENSE_NX, DENSE_M);
+  if (N == 0) return CLIK_OK;
+  if (!h || (m > 0 && (!A || !lb || !ub)) || !sol) return fail(CLIK_ERR_INVALID, "NULL argument");
+  CK(cudaSetDevice(device));
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int block = 64;
+  int grid = (int)std::min<int64_t>((N + block - 1) / block, (int64_t)sms * 8);
+  int mi = max_iter > 0 ? max_iter : 10 * (nx + m);
+  clik_qp_dense_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(N, nx, m, h, A, lb, ub, x0, sol,
+                                                                 status, active, mi);
+  CK(cudaGetLastError());
+  return CLIK_OK;
+}
+
+clik_status clik_pinv_step_host(const clik_skill* cs, int64_t N, const double* t, int32_t t_stride,
+                                const double* q, const double* x, const double* y, double* qdot,
+                                double* xdot, int32_t* mode) {
+  clik_skill* s = const_cast<clik_skill*>(cs);
+  clik_status st = check_common(s, N, t, q, x, y);
+  if (st != CLIK_OK || N == 0) return st;
+  if (!qdot) return fail(CLIK_ERR_INVALID, "qdot is required");
+  const clik_skill_desc& d = s->desc;
+  std::vector<Field> f;
+  f.push_back({t, nullptr, 1, 8, t_stride ? 1 : 0, 0});
+  f.push_back({q, nullptr, d.n_robot, 8, 1, 0});
+  f.push_back({d.n_virtual ? x : nullptr, nullptr, d.n_virtual, 8, 1, 0});
+  f.push_back({d.n_input ? y : nullptr, nullptr, d.n_input, 8, 1, 0});
+  f.push_back({nullptr, qdot, d.n_robot, 8, 1, 0});
+  f.push_back({nullptr, d.n_virtual ? xdot : nullptr, d.n_virtual, 8, 1, 0});
+  f.push_back({nullptr, mode, 1, 4, 1, 0});
+  return run_host_pipeline(s, N, f, [&](char* base, int64_t c, cudaStream_t stream) {
+    return clik_pinv_step(s, c, (const double*)(base + f[0].dev_off), t_stride,
+                          (const double*)(base + f[1].dev_off),
+                          d.n_virtual ? (const double*)(base + f[2].dev_off) : nullptr,
+                          d.n_input ? (const double*)(base + f[3].dev_off) : nullptr,
+                          (double*)(base + f[4].dev_off),
+                          d.n_virtual ? (double*)(base + f[5].dev_off) : nullptr,
+                          mode ? (int32_t*)(base + f[6].dev_off) : nullptr, stream);
+  });
+}
+
+clik_status clik_qp_step_host(const clik_skill* cs, int64_t N, const double* t, int32_t t_stride,
+                              const double* q, const double* x, const double* y, const double* x0,
+                              double* sol, int32_t* status, uint32_t* active, int32_t max_iter) {
+  clik_skill* s = const_cast<clik_skill*>(cs);
+  clik_status st = check_common(s, N, t, q, x, y);
+  if (st != CLIK_OK || N == 0) return st;
+  if (!sol) return fail(CLIK_ERR_INVALID, "sol is required");
+  const clik_skill_desc& d = s->desc;
+  std::vector<Field> f;
+  f.push_back({t, nullptr, 1, 8, t_stride ? 1 : 0, 0});
+  f.push_back({q, nullptr, d.n_robot, 8, 1, 0});
+  f.push_back({d.n_virtual ? x : nullptr, nullptr, d.n_virtual, 8, 1, 0});
+  f.push_back({d.n_input ? y : nullptr, nullptr, d.n_input, 8, 1, 0});
+  f.push_back({x0, nullptr, d.qp_n, 8, 1, 0});
+  f.push_back({nullptr, sol, d.qp_n, 8, 1, 0});
+  f.push_back({nullptr, status, 1, 4, 1, 0});
+  f.push_back({nullptr, active, 2, 4, 1, 0});
+  return run_host_pipeline(s, N, f, [&](char* base, int64_t c, cudaStream_t stream) {
+    return clik_qp_step(s, c, (const double*)(base + f[0].dev_off), t_stride,
+                        (const double*)(base + f[1].dev_off),
+                        d.n_virtual ? (const double*)(base + f[2].dev_off) : nullptr,
+                        d.n_input ? (const double*)(base + f[3].dev_off) : nullptr,
+                        x0 ? (const double*)(base + f[4].dev_off) : nullptr,
+                        (double*)(base + f[5].dev_off),
+                        status ? (int32_t*)(base + f[6].dev_off) : nullptr,
+                        active ? (uint32_t*)(base + f[7].dev_off) : nullptr, max_iter, stream);
+  });
+}
+
+clik_status clik_measure_fp64_peak(int32_t device, int32_t iters, double* tflops) {
+  if (!tflops || iters <= 0) return fail(CLIK_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(device));
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int block = 256, grid = sms * 8;
+  double* out = nullptr;
+  CK(cudaMalloc(&out, (size_t)grid * block * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(e0));
+    dfma_peak_kernel<<<grid, block>>>(out, iters, 0.999999, 1e-7);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * (double)iters * grid * block;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return CLIK_OK;
+}
+
+clik_status clik_flush_l2(int32_t device, void* stream) {
+  if (device < 0 || device >= 64) return fail(CLIK_ERR_INVALID, "bad device");
+  CK(cudaSetDevice(device));
+  {
+    std::lock_guard<std::mutex> lock(g_flush_mu);
+    if (!g_flush_buf[device]) CK(cudaMalloc(&g_flush_buf[device], FLUSH_BYTES));
+  }
+  fill_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(g_flush_buf[device], FLUSH_BYTES / 8, 0.0);
+  CK(cudaGetLastError());
+  return CLIK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,437 @@
+// clik_pinv.cuh — batched singularity-robust multiple-task-priority (SRMTP) pseudo-inverse step with
+// set-based task activation, one controller instance per thread, fp64, sm_100a.
+//
+// Replaces, for N independent instances at once, what the reference does per instance with a
+// Python loop over JIT-compiled CasADi functions:
+//   PseudoInverseController.pinv                      reference casclik/controllers/pseudo_inverse.py:92-105
+//   PseudoInverseController.get_problem_expressions   :259-451  (per-mode velocity)
+//   PseudoInverseController.get_in_tangent_cone_function :132-190
+//   PseudoInverseController.solve                     :512-556  (mode search, fallback zeros / -1)
+//
+// The skill-specific part (constraint values, Jacobians, desired task rates) is straight-line
+// code emitted by casclik_b200/codegen as `S::eval`; this header is the hand-written algebra
+// around it.  `S` also carries the compile-time skill description (sizes, constraint table,
+// Jacobian sparsity, damping), so every loop below has constant bounds and fully unrolls: in the
+// common path all matrices live in registers.
+//
+// Algebra.  The reference forms P(J) = J'(JJ'+lam I)^-1 (wide) or (J'J+lam I)^-1 J' (tall)
+// explicitly and multiplies matrices; here P(J) is only ever applied to a vector (one SPD
+// factorisation + one right-hand side), which is the same arithmetic up to association.  The
+// reference's contract-relevant quirks are kept: the first
+// EqualityConstraint is applied twice (A1), "first" means an empty active list (A2), the
+// null-space projector is rebuilt from the stacked Jacobians with the damped inverse (A3), the
+// in-tangent-cone test uses the 1e-12 thresholds of the code, not of the docstring (A4), active
+// sets contribute no velocity (A5), VelocitySetConstraints are ignored (A6).
+#pragma once
+#include <cstdint>
+
+namespace clik {
+
+enum : int { KIND_EQ = 0, KIND_SET = 1, KIND_VELEQ = 2, KIND_VELSET = 3 };
+
+template <int A, int B> struct Max { static constexpr int v = A > B ? A : B; };
+
+// Everything S::eval produces for one instance.  Unused members are never touched, so after
+// scalar replacement they cost nothing.
+template <class S> struct PinvData {
+  double J[Max<S::M * S::NS, 1>::v];   // stacked constraint Jacobians, row-major, M x NS
+  double des[Max<S::M, 1>::v];         // Eq: -K e - de/dt ; VelEq: target - de/dt
+  double e[Max<S::M, 1>::v];           // Set rows: expression value
+  double jt[Max<S::M, 1>::v];          // Set rows: de/dt
+  double smin[Max<S::M, 1>::v];        // Set rows: bounds
+  double smax[Max<S::M, 1>::v];
+};
+
+// ---- compile-time row lists ------------------------------------------------------------------
+template <int... R> struct Rows {
+  static constexpr int size = sizeof...(R);
+  __host__ __device__ static constexpr int get(int i) {
+    constexpr int a[sizeof...(R) + 1] = {R..., 0};
+    return a[i];
+  }
+};
+template <class A, class B> struct Concat;
+template <int... X, int... Y> struct Concat<Rows<X...>, Rows<Y...>> { using type = Rows<X..., Y...>; };
+template <int R0, int N, int... Acc> struct Range { using type = typename Range<R0, N - 1, R0 + N - 1, Acc...>::type; };
+template <int R0, int... Acc> struct Range<R0, 0, Acc...> { using type = Rows<Acc...>; };
+
+// ---- SPD solve in registers (Cholesky, packed lower triangle) -------------------------------------
+// G: packed lower triangle, G[i*(i+1)/2 + j], j <= i.  b is overwritten with the solution.
+template <int K> __device__ __forceinline__ void spd_solve(double (&G)[K * (K + 1) / 2], double (&b)[K]) {
+  double r[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    double s = G[j * (j + 1) / 2 + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s = fma(-G[j * (j + 1) / 2 + k], G[j * (j + 1) / 2 + k], s);
+    r[j] = rsqrt(s);
+#pragma unroll
+    for (int i = j + 1; i < K; ++i) {
+      double t = G[i * (i + 1) / 2 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t = fma(-G[i * (i + 1) / 2 + k], G[j * (j + 1) / 2 + k], t);
+      G[i * (i + 1) / 2 + j] = t * r[j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    double s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s = fma(-G[i * (i + 1) / 2 + k], b[k], s);
+    b[i] = s * r[i];
+  }
+#pragma unroll
+  for (int i = K - 1; i >= 0; --i) {
+    double s = b[i];
+#pragma unroll
+    for (int k = i + 1; k < K; ++k) s = fma(-G[k * (k + 1) / 2 + i], b[k], s);
+    b[i] = s * r[i];
+  }
+}
+
+// ---- P(J_rows) * b for a compile-time row list -----------------------------------------------------
+// wide  (cols >= rows): J' (J J' + lam I)^-1 b          reference pseudo_inverse.py:97-100
+// tall  (cols <  rows): (J' J + lam I)^-1 J' b          reference pseudo_inverse.py:101-104
+// "standard" (cs.pinv): same two branches, lam = 0, square matrices take the tall branch.
+template <class S, class R>
+__device__ __forceinline__ void pinv_times(const double (&J)[Max<S::M * S::NS, 1>::v],
+                                           const double (&b)[Max<R::size, 1>::v], double (&out)[S::NS]) {
+  constexpr int K = R::size;
+  constexpr int NS = S::NS;
+  constexpr bool wide = S::DAMPED ? (NS >= K) : (K < NS);
+  constexpr double lam = S::DAMPED ? S::LAMBDA : 0.0;
+  if constexpr (wide) {
+    double G[K * (K + 1) / 2];
+    double z[K];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+#pragma unroll
+      for (int c = 0; c <= a; ++c) {
+        double acc = 0.0;
+        bool first = true;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          if (S::jnz(R::get(a), j) && S::jnz(R::get(c), j)) {
+            const double p = J[R::get(a) * NS + j], q = J[R::get(c) * NS + j];
+            acc = first ? p * q : fma(p, q, acc);
+            first = false;
+          }
+        }
+        G[a * (a + 1) / 2 + c] = (a == c) ? acc + lam : acc;
+      }
+      z[a] = b[a];
+    }
+    spd_solve<K>(G, z);
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      double acc = 0.0;
+      bool first = true;
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+        if (S::jnz(R::get(a), j)) {
+          acc = first ? J[R::get(a) * NS + j] * z[a] : fma(J[R::get(a) * NS + j], z[a], acc);
+          first = false;
+        }
+      }
+      out[j] = acc;
+    }
+  } else {
+    double G[NS * (NS + 1) / 2];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+#pragma unroll
+      for (int c = 0; c <= i; ++c) {
+        double acc = 0.0;
+        bool first = true;
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+          if (S::jnz(R::get(a), i) && S::jnz(R::get(a), c)) {
+            const double p = J[R::get(a) * NS + i], q = J[R::get(a) * NS + c];
+            acc = first ? p * q : fma(p, q, acc);
+            first = false;
+          }
+        }
+        G[i * (i + 1) / 2 + c] = (i == c) ? acc + lam : acc;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      double acc = 0.0;
+      bool first = true;
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+        if (S::jnz(R::get(a), j)) {
+          acc = first ? J[R::get(a) * NS + j] * b[a] : fma(J[R::get(a) * NS + j], b[a], acc);
+          first = false;
+        }
+      }
+      out[j] = acc;
+    }
+    spd_solve<NS>(G, out);
+  }
+}
+
+// x <- (I - P(J_rows) J_rows) x        reference pseudo_inverse.py:387-393 (rJ = J without multidim sets)
+template <class S, class R>
+__device__ __forceinline__ void nullspace_apply(const double (&J)[Max<S::M * S::NS, 1>::v], double (&x)[S::NS]) {
+  constexpr int K = R::size;
+  constexpr int NS = S::NS;
+  double b[Max<K, 1>::v];
+#pragma unroll
+  for (int a = 0; a < K; ++a) {
+    double acc = 0.0;
+    bool first = true;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      if (S::jnz(R::get(a), j)) {
+        acc = first ? J[R::get(a) * NS + j] * x[j] : fma(J[R::get(a) * NS + j], x[j], acc);
+        first = false;
+      }
+    }
+    b[a] = acc;
+  }
+  double corr[NS];
+  pinv_times<S, R>(J, b, corr);
+#pragma unroll
+  for (int j = 0; j < NS; ++j) x[j] -= corr[j];
+}
+
+// ---- one mode, mode mask known at compile time -----------------------------------------------------
+// Walks the priority-sorted constraint table exactly like the reference's loop
+// (pseudo_inverse.py:274-443), with the active-row list carried as a type.
+template <class S, unsigned MASK, int C, class Stack> struct StaticMode {
+  __device__ __forceinline__ static void run(const PinvData<S>& d, double (&v)[S::NS]) {
+    if constexpr (C < S::NC) {
+      constexpr int kind = S::kind(C);
+      constexpr int r0 = S::row0(C);
+      constexpr int m = S::rows(C);
+      using RC = typename Range<r0, m>::type;
+      if constexpr (kind == KIND_EQ || kind == KIND_VELEQ) {
+        double b[Max<m, 1>::v];
+#pragma unroll
+        for (int a = 0; a < m; ++a) b[a] = d.des[r0 + a];
+        double w[S::NS];
+        pinv_times<S, RC>(d.J, b, w);
+        if constexpr (Stack::size == 0) {
+#pragma unroll
+          for (int j = 0; j < S::NS; ++j) v[j] += w[j];                 // :322-326 / :331-335
+          using S1 = typename Concat<Stack, RC>::type;
+          if constexpr (kind == KIND_EQ) {                                // falls into :382-396 as well
+            nullspace_apply<S, S1>(d.J, w);
+#pragma unroll
+            for (int j = 0; j < S::NS; ++j) v[j] += w[j];
+            StaticMode<S, MASK, C + 1, typename Concat<S1, RC>::type>::run(d, v);
+          } else {
+            StaticMode<S, MASK, C + 1, S1>::run(d, v);
+          }
+        } else {
+          nullspace_apply<S, Stack>(d.J, w);                              // :387-394 / :434-441
+#pragma unroll
+          for (int j = 0; j < S::NS; ++j) v[j] += w[j];
+          StaticMode<S, MASK, C + 1, typename Concat<Stack, RC>::type>::run(d, v);
+        }
+      } else if constexpr (kind == KIND_SET) {
+        if constexpr ((MASK >> S::set_index(C)) & 1u) {                   // :399-405
+          StaticMode<S, MASK, C + 1, typename Concat<Stack, RC>::type>::run(d, v);
+        } else {
+          StaticMode<S, MASK, C + 1, Stack>::run(d, v);
+        }
+      } else {
+        StaticMode<S, MASK, C + 1, Stack>::run(d, v);                     // VelocitySet: ignored
+      }
+    }
+  }
+};
+
+// in-tangent-cone test of one scalar set (reference pseudo_inverse.py:151-185)
+__device__ __forceinline__ bool in_tangent_cone(double e, double de, double smin, double smax) {
+  return (smin - e < 1e-12) ? ((e - smax < 1e-12) ? true : (de < 0.0)) : (de > 0.0);
+}
+
+template <class S, unsigned MASK>
+__device__ __forceinline__ bool static_mode(const PinvData<S>& d, double (&v)[S::NS]) {
+#pragma unroll
+  for (int j = 0; j < S::NS; ++j) v[j] = 0.0;
+  StaticMode<S, MASK, 0, Rows<>>::run(d, v);
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < S::NC; ++c) {
+    if (S::kind(c) == KIND_SET && !((MASK >> S::set_index(c)) & 1u)) {
+      const int r = S::row0(c);
+      double dot = 0.0;
+      bool first = true;
+#pragma unroll
+      for (int j = 0; j < S::NS; ++j) {
+        if (S::jnz(r, j)) {
+          dot = first ? d.J[r * S::NS + j] * v[j] : fma(d.J[r * S::NS + j], v[j], dot);
+          first = false;
+        }
+      }
+      ok = ok && in_tangent_cone(d.e[r], d.jt[r] + dot, d.smin[r], d.smax[r]);
+    }
+  }
+  return ok;
+}
+
+// ---- one mode, mode mask known only at run time (the rare path) -------------------------------------
+// Same algebra with run-time loops over a row list held in local memory.  Only instances whose
+// mode 0 is rejected come here.
+template <class S>
+__device__ void dyn_pinv_times(const double* J, const int* rows, int K, const double* b, double* out) {
+  constexpr int NS = S::NS;
+  constexpr int D = NS;   // wide: K <= NS ; tall: NS
+  double G[D * (D + 1) / 2];
+  double z[D];
+  double r[D];
+  const bool wide = S::DAMPED ? (NS >= K) : (K < NS);
+  const double lam = S::DAMPED ? S::LAMBDA : 0.0;
+  int n;
+  if (wide) {
+    n = K;
+    for (int a = 0; a < K; ++a) {
+      for (int c = 0; c <= a; ++c) {
+        double acc = 0.0;
+        for (int j = 0; j < NS; ++j) acc = fma(J[rows[a] * NS + j], J[rows[c] * NS + j], acc);
+        G[a * (a + 1) / 2 + c] = (a == c) ? acc + lam : acc;
+      }
+      z[a] = b[a];
+    }
+  } else {
+    n = NS;
+    for (int i = 0; i < NS; ++i) {
+      for (int c = 0; c <= i; ++c) {
+        double acc = 0.0;
+        for (int a = 0; a < K; ++a) acc = fma(J[rows[a] * NS + i], J[rows[a] * NS + c], acc);
+        G[i * (i + 1) / 2 + c] = (i == c) ? acc + lam : acc;
+      }
+      double acc = 0.0;
+      for (int a = 0; a < K; ++a) acc = fma(J[rows[a] * NS + i], b[a], acc);
+      z[i] = acc;
+    }
+  }
+  for (int j = 0; j < n; ++j) {
+    double s = G[j * (j + 1) / 2 + j];
+    for (int k = 0; k < j; ++k) s = fma(-G[j * (j + 1) / 2 + k], G[j * (j + 1) / 2 + k], s);
+    r[j] = rsqrt(s);
+    for (int i = j + 1; i < n; ++i) {
+      double t = G[i * (i + 1) / 2 + j];
+      for (int k = 0; k < j; ++k) t = fma(-G[i * (i + 1) / 2 + k], G[j * (j + 1) / 2 + k], t);
+      G[i * (i + 1) / 2 + j] = t * r[j];
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    double s = z[i];
+    for (int k = 0; k < i; ++k) s = fma(-G[i * (i + 1) / 2 + k], z[k], s);
+    z[i] = s * r[i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = z[i];
+    for (int k = i + 1; k < n; ++k) s = fma(-G[k * (k + 1) / 2 + i], z[k], s);
+    z[i] = s * r[i];
+  }
+  if (wide) {
+    for (int j = 0; j < NS; ++j) {
+      double acc = 0.0;
+      for (int a = 0; a < K; ++a) acc = fma(J[rows[a] * NS + j], z[a], acc);
+      out[j] = acc;
+    }
+  } else {
+    for (int j = 0; j < NS; ++j) out[j] = z[j];
+  }
+}
+
+template <class S>
+__device__ __noinline__ bool dynamic_mode(const PinvData<S>* d, unsigned mask, double* v) {
+  constexpr int NS = S::NS;
+  constexpr int MAXK = S::M + S::MAXROWS;   // every row once + the doubled first equality
+  int stack[MAXK];
+  int k = 0;
+  double w[NS], corr[NS], b[Max<MAXK, 1>::v];
+  for (int j = 0; j < NS; ++j) v[j] = 0.0;
+  for (int c = 0; c < S::NC; ++c) {
+    const int kind = S::kind(c), r0 = S::row0(c), m = S::rows(c);
+    if (kind == KIND_EQ || kind == KIND_VELEQ) {
+      int own[S::MAXROWS];
+      for (int a = 0; a < m; ++a) own[a] = r0 + a;
+      dyn_pinv_times<S>(d->J, own, m, &d->des[r0], w);
+      const bool first = (k == 0);
+      if (first) {
+        for (int j = 0; j < NS; ++j) v[j] += w[j];
+        for (int a = 0; a < m; ++a) stack[k++] = r0 + a;
+      }
+      if (!first || kind == KIND_EQ) {
+        for (int a = 0; a < k; ++a) {
+          double acc = 0.0;
+          for (int j = 0; j < NS; ++j) acc = fma(d->J[stack[a] * NS + j], w[j], acc);
+          b[a] = acc;
+        }
+        dyn_pinv_times<S>(d->J, stack, k, b, corr);
+        for (int j = 0; j < NS; ++j) v[j] += w[j] - corr[j];
+        for (int a = 0; a < m; ++a) stack[k++] = r0 + a;
+      }
+    } else if (kind == KIND_SET) {
+      if ((mask >> S::set_index(c)) & 1u) stack[k++] = r0;
+    }
+  }
+  bool ok = true;
+  for (int c = 0; c < S::NC; ++c) {
+    if (S::kind(c) == KIND_SET && !((mask >> S::set_index(c)) & 1u)) {
+      const int r = S::row0(c);
+      double dot = 0.0;
+      for (int j = 0; j < NS; ++j) dot = fma(d->J[r * NS + j], v[j], dot);
+      ok = ok && in_tangent_cone(d->e[r], d->jt[r] + dot, d->smin[r], d->smax[r]);
+    }
+  }
+  return ok;
+}
+
+// ---- the step --------------------------------------------------------------------------------------
+// Structure-of-arrays batch: q[j*N + i] is coordinate j of instance i (same for x, y, outputs), so
+// consecutive threads touch consecutive addresses.  t has stride t_stride (0 = one shared time).
+// mode[i] = index into the activation map of the accepted mode, -1 (and zero velocity) if none.
+template <class S>
+__device__ __forceinline__ void pinv_step(long long N, const double* __restrict__ t, int t_stride,
+                                          const double* __restrict__ q, const double* __restrict__ x,
+                                          const double* __restrict__ y, double* __restrict__ qdot,
+                                          double* __restrict__ xdot, int* __restrict__ mode) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    double qv[Max<S::NQ, 1>::v], xv[Max<S::NX, 1>::v], yv[Max<S::NY, 1>::v];
+    const double tv = __ldcs(t + (long long)t_stride * i);
+#pragma unroll
+    for (int j = 0; j < S::NQ; ++j) qv[j] = __ldcs(q + (long long)j * N + i);
+#pragma unroll
+    for (int j = 0; j < S::NX; ++j) xv[j] = __ldcs(x + (long long)j * N + i);
+#pragma unroll
+    for (int j = 0; j < S::NY; ++j) yv[j] = __ldcs(y + (long long)j * N + i);
+
+    PinvData<S> d;
+    S::eval(tv, qv, xv, yv, d);
+
+    double v[S::NS];
+    int accepted = 0;
+    bool ok = static_mode<S, 0u>(d, v);
+    if constexpr (S::NSETS > 0) {
+      if (!ok) {
+        accepted = -1;
+        PinvData<S> copy = d;     // the slow path indexes dynamically: keep `d` itself in registers
+        double vd[S::NS];
+        for (int mi = 1; mi < S::NMODES; ++mi) {
+          if (dynamic_mode<S>(&copy, S::mode_mask(mi), vd)) {
+            accepted = mi;
+            break;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < S::NS; ++j) v[j] = (accepted < 0) ? 0.0 : vd[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < S::NQ; ++j) __stcs(qdot + (long long)j * N + i, v[j]);
+#pragma unroll
+    for (int j = 0; j < S::NX; ++j) __stcs(xdot + (long long)j * N + i, v[S::NQ + j]);
+    if (mode != nullptr) __stcs(mode + i, accepted);
+  }
+}
+
+}  // namespace clik

@@ -1,0 +1,219 @@
+// clik_qp.cuh — batched dense strictly-convex QP for the reactive-QP controller step, one
+// instance per thread, fp64, sm_100a.
+//
+//     min 1/2 x' diag(h) x      s.t.  lb <= A x <= ub            x = [robot vel; virtual vel; slack]
+//
+// This is the problem the reference assembles in ReactiveQPController.get_cost_expr /
+// get_constraints_expr (reference casclik/controllers/reactive_qp.py:175-246) and hands to
+// qpOASES through cs.conic (:256-260, :493, :512-513).  h > 0 (mu*w, mu + w_slack), so the
+// minimiser is unique and any exact method returns the point qpOASES converges to.
+//
+// Method: Goldfarb-Idnani dual active set in the coordinates z = sqrt(h) .* x, where the
+// objective is 1/2 |z|^2 and there is no linear term (the reference never passes g).  z starts at
+// the unconstrained minimiser 0; each outer iteration picks the most violated one-sided
+// constraint and walks to it along the projection of its normal onto the null space of the active
+// normals, dropping active constraints whose multiplier would turn negative.  The active normals
+// are re-orthogonalised from scratch (modified Gram-Schmidt, at most NX columns) whenever the
+// working set changes: the matrices are tiny (UR5 config: 9 x 15) and it keeps the projection
+// accurate without squaring the condition number.  The iteration count is capped (status 1).
+//
+// Outputs per instance: x, status (0 solved, 1 iteration cap, 2 infeasible), and two bit masks
+// of the rows active at their upper / lower bound in the final working set.
+#pragma once
+#include <cstdint>
+#include <cmath>
+
+namespace clik {
+
+enum : int { QP_OK = 0, QP_MAXITER = 1, QP_INFEASIBLE = 2 };
+
+// NXM / MM: compile-time capacities; nx / m: actual sizes (compile-time constants when inlined
+// into a fused skill kernel).  A is row-major m x nx and is overwritten with the scaled rows.
+template <int NXM, int MM>
+__device__ int qp_dual_active_set(const int nx, const int m, double* A, const double* lb,
+                                  const double* ub, const double* h, const double* x0, double* x,
+                                  unsigned* act_up, unsigned* act_lo, const int max_iter) {
+  double s[NXM], z[NXM], d[NXM], np_[NXM], c[NXM], rr[NXM], u[NXM];
+  double Qb[NXM * NXM];   // orthonormal basis of the active normals, column a at Qb[a*nx .. )
+  double R[NXM * NXM];    // upper triangular, R[l*NXM + a]
+  int W[NXM];
+  signed char state[MM];
+  int k = 0;
+
+  for (int j = 0; j < nx; ++j) {
+    s[j] = rsqrt(h[j]);
+    z[j] = 0.0;
+  }
+  for (int i = 0; i < m; ++i) {
+    state[i] = 0;
+    for (int j = 0; j < nx; ++j) A[i * nx + j] *= s[j];
+  }
+  (void)x0;  // primal warm start: the dual method restarts from z = 0 (result is independent of x0)
+
+  int status = QP_MAXITER;
+  bool need_qr = false;
+  for (int it = 0; it < max_iter; ++it) {
+    // ---- most violated one-sided constraint ------------------------------------------------
+    int p = -1;
+    double sp = 0.0, vbest = 0.0;
+    for (int i = 0; i < m; ++i) {
+      if (state[i] != 0) continue;
+      double r = 0.0;
+      for (int j = 0; j < nx; ++j) r = fma(A[i * nx + j], z[j], r);
+      const double vu = r - ub[i], vl = lb[i] - r;
+      const double tu = 1e-12 * fmax(1.0, fabs(ub[i])), tl = 1e-12 * fmax(1.0, fabs(lb[i]));
+      if (vu > tu && vu > vbest) { vbest = vu; p = i; sp = 1.0; }
+      if (vl > tl && vl > vbest) { vbest = vl; p = i; sp = -1.0; }
+    }
+    if (p < 0) { status = QP_OK; break; }
+
+    double nn = 0.0;
+    for (int j = 0; j < nx; ++j) { np_[j] = sp * A[p * nx + j]; nn = fma(np_[j], np_[j], nn); }
+    double up = 0.0;
+    bool done = false, infeasible = false;
+    while (!done) {
+      // ---- (re)factor the active normals: N = Qb R ----------------------------------------
+      if (need_qr) {
+        for (int a = 0; a < k; ++a) {
+          const double sg = (double)state[W[a]];
+          double* col = &Qb[a * nx];
+          for (int j = 0; j < nx; ++j) col[j] = sg * A[W[a] * nx + j];
+          for (int pass = 0; pass < 2; ++pass) {
+            for (int l = 0; l < a; ++l) {
+              double dt = 0.0;
+              for (int j = 0; j < nx; ++j) dt = fma(Qb[l * nx + j], col[j], dt);
+              for (int j = 0; j < nx; ++j) col[j] = fma(-dt, Qb[l * nx + j], col[j]);
+              R[l * NXM + a] = (pass == 0) ? dt : R[l * NXM + a] + dt;
+            }
+          }
+          double nrm = 0.0;
+          for (int j = 0; j < nx; ++j) nrm = fma(col[j], col[j], nrm);
+          nrm = sqrt(nrm);
+          R[a * NXM + a] = nrm;
+          const double inv = 1.0 / nrm;
+          for (int j = 0; j < nx; ++j) col[j] *= inv;
+        }
+        need_qr = false;
+      }
+      // ---- d = (I - Qb Qb') n_p ,  r = R^-1 Qb' n_p ------------------------------------------
+      for (int j = 0; j < nx; ++j) d[j] = np_[j];
+      for (int a = 0; a < k; ++a) c[a] = 0.0;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int a = 0; a < k; ++a) {
+          double dt = 0.0;
+          for (int j = 0; j < nx; ++j) dt = fma(Qb[a * nx + j], d[j], dt);
+          for (int j = 0; j < nx; ++j) d[j] = fma(-dt, Qb[a * nx + j], d[j]);
+          c[a] += dt;
+        }
+      }
+      for (int a = k - 1; a >= 0; --a) {
+        double acc = c[a];
+        for (int l = a + 1; l < k; ++l) acc = fma(-R[a * NXM + l], rr[l], acc);
+        rr[a] = acc / R[a * NXM + a];
+      }
+      double dn = 0.0;
+      for (int j = 0; j < nx; ++j) dn = fma(d[j], d[j], dn);
+      // ---- step lengths -----------------------------------------------------------------------
+      double rmax = 0.0;
+      for (int a = 0; a < k; ++a) rmax = fmax(rmax, fabs(rr[a]));
+      double t1 = INFINITY;
+      int drop = -1;
+      for (int a = 0; a < k; ++a) {
+        if (rr[a] > 1e-12 * rmax && rr[a] > 0.0) {
+          const double cand = u[a] / rr[a];
+          if (cand < t1) { t1 = cand; drop = a; }
+        }
+      }
+      double rp = 0.0;
+      for (int j = 0; j < nx; ++j) rp = fma(A[p * nx + j], z[j], rp);
+      const double viol = (sp > 0.0) ? (rp - ub[p]) : (lb[p] - rp);
+      const bool independent = (k < nx) && (dn > 1e-24 * nn);
+      const double t2 = independent ? viol / dn : INFINITY;
+      const double t = fmin(t1, t2);
+      if (!(t < INFINITY)) { infeasible = true; break; }
+      if (independent) {
+        for (int j = 0; j < nx; ++j) z[j] = fma(-t, d[j], z[j]);
+      }
+      for (int a = 0; a < k; ++a) u[a] = fma(-t, rr[a], u[a]);
+      up += t;
+      if (t2 <= t1) {
+        // full step: p joins the working set; extend the factorisation by one column
+        W[k] = p;
+        state[p] = (sp > 0.0) ? 1 : -1;
+        u[k] = up;
+        for (int a = 0; a < k; ++a) R[a * NXM + k] = c[a];
+        const double nrm = sqrt(dn);
+        R[k * NXM + k] = nrm;
+        const double inv = 1.0 / nrm;
+        for (int j = 0; j < nx; ++j) Qb[k * nx + j] = d[j] * inv;
+        ++k;
+        done = true;
+      } else {
+        // partial step: drop the blocking constraint and try again with the same p
+        state[W[drop]] = 0;
+        for (int a = drop; a < k - 1; ++a) { W[a] = W[a + 1]; u[a] = u[a + 1]; }
+        --k;
+        need_qr = true;
+      }
+    }
+    if (infeasible) { status = QP_INFEASIBLE; break; }
+  }
+
+  for (int j = 0; j < nx; ++j) x[j] = z[j] * s[j];
+  unsigned mu = 0u, ml = 0u;
+  for (int a = 0; a < k; ++a) {
+    if (W[a] < 32) {
+      if (state[W[a]] > 0) mu |= 1u << W[a]; else ml |= 1u << W[a];
+    }
+  }
+  *act_up = mu;
+  *act_lo = ml;
+  return status;
+}
+
+// Everything S::eval_qp produces for one instance.
+template <class S> struct QpData {
+  double A[S::QM * S::QN];
+  double lb[S::QM];
+  double ub[S::QM];
+  double h[S::QN];
+};
+
+// Fused step: evaluate the skill's QP matrices and solve, SoA in / SoA out.
+// sol[j*N + i] is entry j of x for instance i; active[i] = upper mask, active[N + i] = lower mask.
+template <class S>
+__device__ __forceinline__ void qp_step(long long N, const double* __restrict__ t, int t_stride,
+                                        const double* __restrict__ q, const double* __restrict__ x,
+                                        const double* __restrict__ y, const double* __restrict__ x0,
+                                        double* __restrict__ sol, int* __restrict__ status,
+                                        unsigned* __restrict__ active, int max_iter) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    double qv[S::NQ > 0 ? S::NQ : 1], xv[S::NX > 0 ? S::NX : 1], yv[S::NY > 0 ? S::NY : 1];
+    const double tv = __ldcs(t + (long long)t_stride * i);
+#pragma unroll
+    for (int j = 0; j < S::NQ; ++j) qv[j] = __ldcs(q + (long long)j * N + i);
+#pragma unroll
+    for (int j = 0; j < S::NX; ++j) xv[j] = __ldcs(x + (long long)j * N + i);
+#pragma unroll
+    for (int j = 0; j < S::NY; ++j) yv[j] = __ldcs(y + (long long)j * N + i);
+    QpData<S> d;
+    S::eval_qp(tv, qv, xv, yv, d);
+    double x0v[S::QN], xs[S::QN];
+    if (x0 != nullptr) {
+      for (int j = 0; j < S::QN; ++j) x0v[j] = x0[(long long)j * N + i];
+    }
+    unsigned mu, ml;
+    const int st = qp_dual_active_set<S::QN, S::QM>(S::QN, S::QM, d.A, d.lb, d.ub, d.h,
+                                                    x0 != nullptr ? x0v : nullptr, xs, &mu, &ml,
+                                                    max_iter);
+    for (int j = 0; j < S::QN; ++j) __stcs(sol + (long long)j * N + i, xs[j]);
+    if (status != nullptr) status[i] = st;
+    if (active != nullptr) {
+      active[i] = mu;
+      active[N + i] = ml;
+    }
+  }
+}
+
+}  // namespace clik

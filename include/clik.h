@@ -1,0 +1,134 @@
+/* clik.h — C ABI of the B200 batched CLIK controller-step engine (libclik_b200.so).
+ *
+ * The reference (mahaarbo/casclik) has no C ABI of its own: its controller step is Python calling
+ * CasADi.  What it *effectively* binds per skill is CasADi's generated-code ABI — one JIT-compiled
+ * function per mode, `cs.Function(..., {"jit": True})` at
+ *     casclik/controllers/pseudo_inverse.py:476-483   (cntrl_var_<mode>)
+ *     casclik/controllers/reactive_qp.py:283-294      (H_func / A_func / Blb_func / Bub_func)
+ * plus the conic plugin call `cs.conic("solver", "qpoases", ...)` at reactive_qp.py:256-260 and
+ * its invocation at :493 / :512-513.  Each entry point below names the reference call it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *   - batch arrays are structure-of-arrays: coordinate j of instance i is at  a[j*N + i];
+ *   - `*_step` entry points take DEVICE pointers and are asynchronous on `stream` (a cudaStream_t
+ *     passed as void*; NULL = legacy default stream); no hidden host synchronisation;
+ *   - `*_step_host` entry points take HOST pointers, run H2D copy -> kernel -> D2H copy in a
+ *     chunked two-stream pipeline and return when the outputs are in host memory;
+ *   - errors are return codes (0 = CLIK_OK) + clik_last_error(); per-instance outcomes are
+ *     status arrays (mode = -1, QP status), never exceptions;
+ *   - a clik_skill is immutable after load and may be used from several host threads as long as
+ *     each call uses its own stream and buffers.
+ */
+#ifndef CLIK_H_
+#define CLIK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLIK_ABI_VERSION 1
+
+typedef enum {
+  CLIK_OK = 0,
+  CLIK_ERR_INVALID = 1,  /* bad argument (NULL where data is required, size mismatch) */
+  CLIK_ERR_CUDA = 2,     /* CUDA runtime error, text in clik_last_error() */
+  CLIK_ERR_IMAGE = 3,    /* cubin does not contain the kernels the descriptor promises */
+  CLIK_ERR_NOGPU = 4     /* no CUDA device / driver */
+} clik_status;
+
+/* Per-instance QP outcome written to `status[i]` by clik_qp_step / clik_qp_dense.
+ * The reference surfaces 1/2 as a RuntimeError out of `self.solver(...)` (reactive_qp.py:493). */
+#define CLIK_QP_SOLVED 0
+#define CLIK_QP_MAXITER 1
+#define CLIK_QP_INFEASIBLE 2
+
+/* Sizes of a compiled skill; must match the constants baked into the cubin (checked at load). */
+typedef struct {
+  int32_t abi_version; /* CLIK_ABI_VERSION */
+  int32_t device;      /* CUDA device ordinal the skill lives on */
+  int32_t n_robot;     /* SkillSpecification.n_robot_var */
+  int32_t n_virtual;   /* n_virtual_var (0 if the skill has none) */
+  int32_t n_input;     /* n_input_var actually read by the kernels (0 if unused) */
+  int32_t n_slack;     /* n_slack_var */
+  int32_t n_modes;     /* 2^S for S SetConstraints; 1 if S = 0 */
+  int32_t has_pinv;    /* cubin exports clik_pinv_kernel */
+  int32_t has_qp;      /* cubin exports clik_qp_kernel */
+  int32_t qp_n;        /* QP variables  nx = n_robot + n_virtual + n_slack */
+  int32_t qp_m;        /* QP rows */
+  int32_t block_threads; /* launch block size the kernels were tuned for (0 = default 128) */
+} clik_skill_desc;
+
+typedef struct clik_skill clik_skill;
+
+/* Load the sm_100a cubin produced by the expression compiler for one skill.
+ * Replaces the reference's per-mode JIT + dlopen (pseudo_inverse.py:474-483,
+ * reactive_qp.py:283-298): one image holds every mode and both controllers' kernels. */
+clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc* desc,
+                            clik_skill** out);
+void clik_skill_free(clik_skill* skill);
+
+/* PseudoInverseController.solve (pseudo_inverse.py:512-556) for N instances.
+ *   t      [N] (t_stride = 1) or [1] (t_stride = 0)          time_var
+ *   q      [n_robot * N]                                      robot_var
+ *   x      [n_virtual * N] or NULL when n_virtual = 0         virtual_var
+ *   y      [n_input * N]   or NULL when n_input = 0           input_var
+ *   qdot   [n_robot * N]   out                                cntrl_rob
+ *   xdot   [n_virtual * N] out, or NULL when n_virtual = 0    cntrl_virt
+ *   mode   [N] out, may be NULL                               current_mode (-1: none admissible, velocities 0) */
+clik_status clik_pinv_step(const clik_skill* skill, int64_t N, const double* t, int32_t t_stride,
+                           const double* q, const double* x, const double* y, double* qdot,
+                           double* xdot, int32_t* mode, void* stream);
+
+/* ReactiveQPController.solve (reactive_qp.py:461-528) for N instances.
+ *   x0     [qp_n * N] primal warm start or NULL (as the reference's x0=, :495-513)
+ *   sol    [qp_n * N] out: [robot vel; virtual vel; slack]
+ *   status [N] out, may be NULL: CLIK_QP_*
+ *   active [2 * N] out, may be NULL: active[i] bit r = row r at its upper bound,
+ *          active[N + i] bit r = row r at its lower bound (rows >= 32 are not reported)
+ *   max_iter <= 0 selects the default cap 10 * (qp_n + qp_m). */
+clik_status clik_qp_step(const clik_skill* skill, int64_t N, const double* t, int32_t t_stride,
+                         const double* q, const double* x, const double* y, const double* x0,
+                         double* sol, int32_t* status, uint32_t* active, int32_t max_iter,
+                         void* stream);
+
+/* The conic call itself, `solver(h=H, a=A, lba=lb, uba=ub[, x0=])` (reactive_qp.py:493), for N
+ * numeric problems of one shape: min 1/2 x' diag(h) x, lb <= A x <= ub.
+ *   h [nx * N], A [(m * nx) * N] row-major per instance (entry (r, c) at A[(r*nx + c)*N + i]),
+ *   lb, ub [m * N].  Limits: nx <= 16, m <= 32.  +-inf bounds are allowed. */
+clik_status clik_qp_dense(int32_t device, int64_t N, int32_t nx, int32_t m, const double* h,
+                          const double* A, const double* lb, const double* ub, const double* x0,
+                          double* sol, int32_t* status, uint32_t* active, int32_t max_iter,
+                          void* stream);
+
+/* Host-buffer variants (same argument meaning, HOST pointers, synchronous). */
+clik_status clik_pinv_step_host(const clik_skill* skill, int64_t N, const double* t,
+                                int32_t t_stride, const double* q, const double* x,
+                                const double* y, double* qdot, double* xdot, int32_t* mode);
+clik_status clik_qp_step_host(const clik_skill* skill, int64_t N, const double* t, int32_t t_stride,
+                              const double* q, const double* x, const double* y, const double* x0,
+                              double* sol, int32_t* status, uint32_t* active, int32_t max_iter);
+
+/* Launch geometry chosen at load time (for reporting). */
+clik_status clik_skill_launch_info(const clik_skill* skill, int32_t which /*0 pinv, 1 qp*/,
+                                   int32_t* grid, int32_t* block, int32_t* regs_per_thread,
+                                   int32_t* local_bytes_per_thread);
+
+/* Measurement helpers used by bench.py (not part of the controller path):
+ * sustained fp64 FMA throughput of the device in TFLOP/s (FMA = 2 flops), measured with
+ * CUDA events over `iters` dependent-chain FMAs per thread on a full grid; and an L2 flush
+ * (writes a buffer larger than L2). */
+clik_status clik_measure_fp64_peak(int32_t device, int32_t iters, double* tflops);
+clik_status clik_flush_l2(int32_t device, void* stream);
+
+int32_t clik_device_count(void);
+int32_t clik_abi_version(void);
+const char* clik_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIK_H_ */

@@ -1,0 +1,206 @@
+"""Parity of the CUDA pseudo-inverse path (through the C ABI) against the oracle, on seeded
+synthetic inputs of the BASELINE.json configs.  Tolerance for joint-velocity commands is the one
+BASELINE.json:north_star states: |a - b| <= 1e-12 + 1e-9*|b| element-wise; mode flags bit-exact."""
+import numpy as np
+import pytest
+
+from oracle_bridge import oracle_pinv, close
+import casclik_b200 as cc
+from casclik_b200 import cs, scenarios
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-9, 1e-12
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available(), "the gpu tests need a CUDA device"
+    return torch
+
+
+def _run_device(ctrl, inp):
+    torch = _torch()
+    dev = torch.device("cuda", 0)
+    up = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    qd, xd, mode = ctrl.solve_batch(up(inp["t"]), up(inp["q"]), up(inp.get("x")), up(inp.get("y")))
+    torch.cuda.synchronize()
+    return qd.cpu().numpy(), (None if xd is None else xd.cpu().numpy()), mode.cpu().numpy()
+
+
+def _setup(name):
+    sc = scenarios.get(name)
+    ctrl = sc.make_controller()
+    ctrl.setup_problem_functions()
+    ctrl.setup_solver()
+    return sc, ctrl
+
+
+def _report(v, ref, what):
+    err = np.abs(v - ref)
+    bad = ~close(v, ref, RTOL, ATOL)
+    rel = err / (np.abs(ref) + 1e-300)
+    return "%s: max abs err %.3e, max rel err %.3e, %d / %d entries out of tolerance" % (
+        what, err.max(), rel[np.abs(ref) > 1e-6].max() if np.any(np.abs(ref) > 1e-6) else 0.0,
+        int(bad.sum()), bad.size)
+
+
+def test_ur5_track_parity_device_and_host_paths():
+    sc, ctrl = _setup("ur5_track")
+    inp = sc.sample(4096, seed=0)
+    ref_v, ref_mode = oracle_pinv(sc.spec, inp)
+    v, _, mode = _run_device(ctrl, inp)
+    assert np.array_equal(mode, ref_mode) and np.all(mode == 0)
+    assert close(v, ref_v, RTOL, ATOL).all(), _report(v, ref_v, "ur5_track device")
+    # host-buffer ABI (pipelined H2D / kernel / D2H) gives the same bits as the device ABI
+    vh, _, mh = ctrl.solve_batch(inp["t"], inp["q"], None, inp["y"])
+    assert np.array_equal(vh, v) and np.array_equal(mh, mode)
+
+
+def test_ur5_track_single_instance_api_matches_reference_conventions():
+    sc, ctrl = _setup("ur5_track")
+    inp = sc.sample(3, seed=5)
+    ref_v, _ = oracle_pinv(sc.spec, inp)
+    for i in range(3):
+        res = ctrl.solve(0.0, inp["q"][:, i], input_var=inp["y"][:, i])
+        assert len(res) == 3 and res[1] is None and res[2] is None
+        got = res[0].toarray()[:, 0]
+        assert got.shape == (6,)
+        assert close(got, ref_v[:, i], RTOL, ATOL).all()
+        assert ctrl.current_mode == 0
+
+
+def test_ragged_and_empty_batches():
+    sc, ctrl = _setup("ur5_track")
+    torch = _torch()
+    for N in (1, 31, 129, 1000):
+        inp = sc.sample(N, seed=N)
+        ref_v, _ = oracle_pinv(sc.spec, inp)
+        v, _, mode = _run_device(ctrl, inp)
+        assert v.shape == (6, N) and close(v, ref_v, RTOL, ATOL).all()
+    q0 = torch.empty((6, 0), dtype=torch.float64, device="cuda")
+    y0 = torch.empty((3, 0), dtype=torch.float64, device="cuda")
+    qd, _, mode = ctrl.solve_batch(0.0, q0, None, y0)
+    assert qd.shape == (6, 0) and mode.shape == (0,)
+
+
+def test_scalar_time_broadcast_equals_per_instance_time():
+    sc, ctrl = _setup("ur5_moe2016_pinv")
+    torch = _torch()
+    inp = sc.sample(512, seed=2)
+    q = torch.from_numpy(inp["q"]).cuda()
+    a = ctrl.solve_batch(17.5, q)
+    b = ctrl.solve_batch(torch.full((512,), 17.5, dtype=torch.float64, device="cuda"), q)
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+
+
+@pytest.mark.parametrize("name", ["ur5_moe2016_pinv", "iiwa_multitask", "iiwa_multitask_stress"])
+def test_set_based_modes_parity(name):
+    sc, ctrl = _setup(name)
+    inp = sc.sample(4096, seed=1)
+    ref_v, ref_mode = oracle_pinv(sc.spec, inp)
+    v, _, mode = _run_device(ctrl, inp)
+    assert len(np.unique(ref_mode)) > 3, "inputs must exercise several modes"
+    assert np.array_equal(mode, ref_mode), "mode flags differ in %d instances" % int((mode != ref_mode).sum())
+    assert close(v, ref_v, RTOL, ATOL).all(), _report(v, ref_v, name)
+
+
+def test_no_admissible_mode_returns_zero_and_minus_one():
+    # p must stay in [0, 1] but the only task pushes it further out and the set itself cannot
+    # produce motion (A5): with p = 2 and target 3 every mode is rejected or ...
+    t, p = cs.MX.sym("t"), cs.MX.sym("p")
+    lim1 = cc.SetConstraint("a", p, set_min=0.0, set_max=1.0, priority=1)
+    lim2 = cc.SetConstraint("b", -p, set_min=-1.0, set_max=0.0, priority=2)
+    eq = cc.EqualityConstraint("go", 3.0 - p, priority=3)
+    spec = cc.SkillSpecification("stuck", t, p, constraints=[lim1, lim2, eq])
+    ctrl = cc.PseudoInverseController(spec)
+    ctrl.setup_solver()
+    inp = {"t": np.zeros(4), "q": np.array([[2.0, 0.5, 2.0, -1.0]])}
+    ref_v, ref_mode = oracle_pinv(spec, inp)
+    v, _, mode = _run_device(ctrl, inp)
+    assert np.array_equal(mode, ref_mode)
+    assert close(v, ref_v, RTOL, ATOL).all()
+    for i in np.nonzero(ref_mode < 0)[0]:
+        assert v[0, i] == 0.0
+
+
+def test_virtual_variable_and_velocity_equality():
+    """Cart path-following skill of the notebooks (virtual path variable x)."""
+    t, p, dp = cs.MX.sym("t"), cs.MX.sym("p"), cs.MX.sym("dp")
+    x, dx = cs.MX.sym("x"), cs.MX.sym("dx")
+    up = cc.EqualityConstraint("move_up_path_cnstr", 300 - x, gain=1.0, priority=1)
+    lim = cc.SetConstraint("cart_limit_cnstr", p, gain=1.0, set_min=0.0, set_max=1.0, priority=1)
+    dist = cc.EqualityConstraint("min_dist_cnstr", 0.4 * cs.sin(0.3 * x) - p, gain=1.0,
+                                 constraint_type="soft", priority=3)
+    vel = cc.VelocityEqualityConstraint("drift", p + 0.1 * x, target=0.05, priority=4)
+    spec = cc.SkillSpecification("path", t, p, robot_vel_var=dp, virtual_var=x, virtual_vel_var=dx,
+                                 constraints=[up, dist, lim, vel])
+    ctrl = cc.PseudoInverseController(spec)
+    ctrl.setup_solver()
+    rng = np.random.default_rng(0)
+    N = 257
+    inp = {"t": np.zeros(N), "q": rng.uniform(-0.2, 1.2, (1, N)), "x": rng.uniform(0, 20, (1, N))}
+    ref_v, ref_mode = oracle_pinv(spec, inp)
+    v, xd, mode = _run_device(ctrl, inp)
+    got = np.vstack([v, xd])
+    assert np.array_equal(mode, ref_mode)
+    assert close(got, ref_v, RTOL, ATOL).all(), _report(got, ref_v, "cart path")
+    r = ctrl.solve(0.0, 0.3, virtual_var=2.0)
+    assert r[1] is not None and r[1].shape == (1, 1)
+
+
+def test_full_size_properties_ur5_track():
+    """Config 2 at its BASELINE size (2^20): properties that do not need the oracle."""
+    sc, ctrl = _setup("ur5_track")
+    torch = _torch()
+    N = 1 << 20
+    inp = sc.sample(N, seed=0)
+    q = torch.from_numpy(inp["q"]).cuda()
+    y = torch.from_numpy(inp["y"]).cuda()
+    v, _, mode = ctrl.solve_batch(0.0, q, None, y)
+    torch.cuda.synchronize()
+    assert bool((mode == 0).all()) and bool(torch.isfinite(v).all())
+    # (1) shard equivalence: any contiguous slice run on its own gives the same bits
+    for lo, hi in ((0, 1000), (12345, 70001), (N - 777, N)):
+        vs, _, ms = ctrl.solve_batch(0.0, q[:, lo:hi].contiguous(), None, y[:, lo:hi].contiguous())
+        assert torch.equal(vs, v[:, lo:hi])
+    # (2) a first-order step along v reduces the task error for a small step (closed-loop sanity)
+    from casclik_b200.sym import dag
+    p_expr = sc.spec.constraints[0].expression
+    nodes = p_expr.nodes()
+    ids_q = [s.id for s in sc.spec.robot_var.nodes()]
+    ids_y = [s.id for s in sc.spec.input_var.nodes()]
+
+    def err(qq):
+        vals = {i: qq[k] for k, i in enumerate(ids_q)}
+        vals.update({i: inp["y"][k] for k, i in enumerate(ids_y)})
+        e = np.stack(dag.evaluate(nodes, vals))
+        return np.sqrt((e * e).sum(axis=0))
+    sub = slice(0, 20000)
+    e0 = err(inp["q"][:, sub])
+    e1 = err(inp["q"][:, sub] + 1e-3 * v[:, sub].cpu().numpy())
+    assert (e1 < e0).mean() > 0.999
+    # (3) oracle on a strided subsample of the full batch
+    idx = np.arange(0, N, 509)
+    ref_v, _ = oracle_pinv(sc.spec, {"t": inp["t"][idx], "q": inp["q"][:, idx], "y": inp["y"][:, idx]})
+    got = v[:, torch.from_numpy(idx).cuda()].cpu().numpy()
+    assert close(got, ref_v, RTOL, ATOL).all(), _report(got, ref_v, "ur5_track 2^20 subsample")
+
+
+def test_damping_option_is_read_at_setup_time():
+    """Appendix A19: notebooks mutate ctrl.options after construction (lambda = 1e-26)."""
+    sc = scenarios.get("ur5_track")
+    ctrl = sc.make_controller()
+    ctrl.options["damping_factor"] = 1e-26
+    ctrl.setup_solver()
+    inp = sc.sample(256, seed=3)
+    ref_v, _ = oracle_pinv(sc.spec, inp, {"damping_factor": 1e-26})
+    v, _, _ = _run_device(ctrl, inp)
+    assert close(v, ref_v, 1e-8, ATOL).all(), _report(v, ref_v, "lambda=1e-26")
+    ctrl2 = sc.make_controller()
+    ctrl2.options["pinv_method"] = "standard"
+    ctrl2.setup_solver()
+    ref_s, _ = oracle_pinv(sc.spec, inp, {"pinv_method": "standard"})
+    v2, _, _ = _run_device(ctrl2, inp)
+    assert close(v2, ref_s, 1e-8, ATOL).all(), _report(v2, ref_s, "standard pinv")
