@@ -7,6 +7,8 @@ csrc/clik_pinv.cuh and csrc/clik_qp.cuh on it.  The same emitter can print plain
 tests to cross-check the emitted text against the NumPy interpreter with gcc).
 """
 import math
+import os
+import struct
 
 from ..sym import dag
 from .lower import KIND_EQ, KIND_SET, KIND_VELEQ
@@ -30,16 +32,29 @@ def literal(v: float) -> str:
 class Emitter(object):
     """Emits the statements computing a set of nodes, sharing temporaries across calls."""
 
-    def __init__(self, sym_names):
+    def __init__(self, sym_names, const_table=None, sincos_name="sincos"):
         self.sym_names = sym_names
         self.name = {}        # node id -> C expression (temp name, symbol name or literal)
         self.lines = []
         self.counter = 0
         self.hist = {}
+        self.const_table = const_table   # list collecting constants that go to the constant bank
+        self.sincos_name = sincos_name
+
+    def _const(self, v):
+        """Constants whose low 32 bits are zero fit an instruction immediate; everything else is
+        read from the __constant__ table (a free operand) instead of being built with two moves."""
+        if self.const_table is None or v != v or math.isinf(v):
+            return literal(v)
+        if struct.unpack("<Q", struct.pack("<d", v))[0] & 0xFFFFFFFF == 0:
+            return literal(v)
+        if v not in self.const_table:
+            self.const_table.append(v)
+        return "KC[%d]" % self.const_table.index(v)
 
     def _ref(self, n):
         if n.op == "const":
-            return literal(n.val)
+            return self._const(n.val)
         if n.op == "sym":
             return self.sym_names[n.id]
         return self.name[n.id]
@@ -69,7 +84,7 @@ class Emitter(object):
             if op in ("sin", "cos") and n.args[0].id in paired:
                 pair = paired[n.args[0].id]
                 s, c = self._tmp(), self._tmp()
-                self.lines.append("double %s, %s; sincos(%s, &%s, &%s);" % (s, c, a[0], s, c))
+                self.lines.append("double %s, %s; %s(%s, &%s, &%s);" % (s, c, self.sincos_name, a[0], s, c))
                 self.name[pair["sin"].id] = s
                 self.name[pair["cos"].id] = c
                 other = pair["cos" if op == "sin" else "sin"]
@@ -116,7 +131,14 @@ class Emitter(object):
 
     def assign(self, lhs, node):
         self.require([node])
+        self.roots = getattr(self, "roots", [])
+        self.roots.append(node)
         self.lines.append("%s = %s;" % (lhs, self._ref(node)))
+
+    def inputs_read(self):
+        """Number of distinct input scalars (t, q_i, x_i, y_i) the emitted program reads: loads of
+        unused inputs are dead code in the kernel, so only these count as algorithmic traffic."""
+        return len(dag.symbols_of(getattr(self, "roots", [])))
 
     def counts(self):
         flops = sum(_FLOP_OPS.get(op, 0) * k for op, k in self.hist.items())
@@ -203,8 +225,16 @@ def _switch(name, values, ret="int"):
             % (ret, name, body))
 
 
-def emit_skill(pinv=None, qp=None, label="skill", block_threads=128, min_blocks=0):
-    """-> (source text, meta dict).  `pinv`: PinvProgram or None, `qp`: QpProgram or None."""
+def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks=None):
+    """-> (source text, meta dict).  `pinv`: PinvProgram or None, `qp`: QpProgram or None.
+    Tuning knobs (also settable through the environment for experiments): CLIK_BLOCK,
+    CLIK_MINBLOCKS, CLIK_CONSTBANK (1), CLIK_FAST_SINCOS (1)."""
+    if block_threads is None:
+        block_threads = int(os.environ.get("CLIK_BLOCK", "128"))
+    if min_blocks is None:
+        min_blocks = int(os.environ.get("CLIK_MINBLOCKS", "0"))
+    const_table = [] if os.environ.get("CLIK_CONSTBANK", "1") == "1" else None
+    sincos_name = "clik::sincos_fast" if os.environ.get("CLIK_FAST_SINCOS", "1") == "1" else "sincos"
     ref = pinv if pinv is not None else qp
     if ref is None:
         raise ValueError("nothing to emit")
@@ -214,6 +244,7 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=128, min_blocks=
             "n_modes": 1, "qp_n": 0, "qp_m": 0, "block_threads": block_threads}
     out = []
     out.append("// generated by casclik_b200.codegen for skill %r -- do not edit" % label)
+    out.append('#include "clik_math.cuh"')
     out.append('#include "clik_pinv.cuh"')
     out.append('#include "clik_qp.cuh"')
     out.append("")
@@ -254,7 +285,7 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=128, min_blocks=
         pre_struct.append("__device__ const unsigned short clik_mode_tab[%d] = {%s};" % (
             len(masks), ", ".join(str(v) for v in masks)))
         out.append("  __device__ static __forceinline__ unsigned mode_mask(int mi) { return clik_mode_tab[mi]; }")
-        em = Emitter(pinv.syms.names)
+        em = Emitter(pinv.syms.names, const_table, sincos_name)
         body = []
         for b in pinv.blocks:
             for r in range(b["rows"]):
@@ -276,14 +307,15 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=128, min_blocks=
         meta["pinv_eval"] = cnt
         meta["pinv_algebra_flops_mode0"] = pinv_mode0_flops(pinv)
         meta["pinv_flops_mode0"] = cnt["flops"] + meta["pinv_algebra_flops_mode0"]
-        meta["pinv_bytes_per_step"] = 8 * (1 + nq + nxv + ny) + 8 * (nq + nxv) + 4
+        meta["pinv_inputs_read"] = em.inputs_read()
+        meta["pinv_bytes_per_step"] = 8 * em.inputs_read() + 8 * (nq + nxv) + 4
         meta["jacobian_nnz"] = sum(bin(v).count("1") for v in rowmask)
         meta["rows"] = pinv.m
 
     if qp is not None:
         meta["qp_n"], meta["qp_m"] = qp.nx, qp.m
         out.append("  static constexpr int QN = %d, QM = %d;" % (qp.nx, qp.m))
-        em = Emitter(qp.syms.names)
+        em = Emitter(qp.syms.names, const_table, sincos_name)
         for r in range(qp.m):
             for j in range(qp.nx):
                 em.assign("d.A[%d]" % (r * qp.nx + j), qp.A[r][j])
@@ -295,10 +327,14 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=128, min_blocks=
         out += ["    " + ln for ln in em.lines]
         out.append("  }")
         meta["qp_eval"] = em.counts()
-        meta["qp_bytes_per_step"] = 8 * (1 + nq + nxv + ny) + 8 * qp.nx + 4 + 8
+        meta["qp_inputs_read"] = em.inputs_read()
+        meta["qp_bytes_per_step"] = 8 * em.inputs_read() + 8 * qp.nx + 4 + 8
 
     out.append("};")
     out.append("")
+    if const_table:
+        pre_struct.append("__constant__ double KC[%d] = {%s};" % (
+            len(const_table), ", ".join(literal(v) for v in const_table)))
     out[struct_at:struct_at] = pre_struct
     bounds = "__launch_bounds__(%d%s)" % (block_threads, (", %d" % min_blocks) if min_blocks else "")
     if pinv is not None:

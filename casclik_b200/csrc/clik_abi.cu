@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -79,7 +80,11 @@ clik_status setup_kernel(clik_skill* s, const char* name, KernelInfo* k) {
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k->kernel, k->block, 0));
   if (per_sm < 1) per_sm = 1;
-  k->grid = s->sm_count * per_sm;
+  // grid cap = resident CTAs x waves.  waves = 1 is a persistent grid-stride launch; 0 lifts the
+  // cap (one CTA per block_threads instances, hardware CTA scheduler balances the tail).
+  int waves = 0;
+  if (const char* w = getenv("CLIK_GRID_WAVES")) waves = atoi(w);
+  k->grid = waves > 0 ? s->sm_count * per_sm * waves : 0x7fffffff;
   return CLIK_OK;
 }
 

@@ -1,0 +1,76 @@
+// clik_math.cuh — fp64 math helpers for the generated skill code.
+//
+// sincos: forward kinematics needs sin and cos of every joint angle (5-7 pairs per controller
+// step), and in the first profile (profiles/r1_pinv_ncu_summary.md) the CUDA library's inlined
+// sincos made up about half of the kernel's instructions, most of them UMOV/IMAD.MOV pairs that
+// materialise 64-bit polynomial coefficients as immediates.  This version keeps the same
+// structure (Cody-Waite reduction by pi/2, two minimax polynomials on [-pi/4, pi/4], quadrant
+// select) but reads every coefficient from the constant bank, where it is a free instruction
+// operand, and leaves arguments outside the fast-reduction range to the library routine.
+//
+// Polynomials: the classic fdlibm __kernel_sin / __kernel_cos coefficient sets (error < 1 ulp on
+// the reduced interval).  Reduction: 3-term Cody-Waite, exact for |x| < ~1e5 (same bound the
+// CUDA library uses for its fast path).
+#pragma once
+
+namespace clik {
+
+__constant__ double SC_TAB[20] = {
+    6.36619772367581382433e-01,   // 0  2/pi
+    1.57079632679489655800e+00,   // 1  pi/2 hi
+    6.12323399573676603587e-17,   // 2  pi/2 mid
+    -1.49738490485916983294e-33,  // 3  pi/2 lo (residual of hi+mid)
+    -1.66666666666666324348e-01,  // 4  S1
+    8.33333333332248946124e-03,   // 5  S2
+    -1.98412698298579493134e-04,  // 6  S3
+    2.75573137070700676789e-06,   // 7  S4
+    -2.50507602534068634195e-08,  // 8  S5
+    1.58969099521155010221e-10,   // 9  S6
+    4.16666666666666019037e-02,   // 10 C1
+    -1.38888888888741095749e-03,  // 11 C2
+    2.48015872894767294178e-05,   // 12 C3
+    -2.75573143513906633035e-07,  // 13 C4
+    2.08757232129817482790e-09,   // 14 C5
+    -1.13596475577881948265e-11,  // 15 C6
+    0.0, 0.0, 0.0, 0.0};
+
+// arguments outside the fast-reduction range (huge, inf, nan): library routine, kept out of line
+__device__ __noinline__ void sincos_slow(double x, double* sp, double* cp) { sincos(x, sp, cp); }
+
+__device__ __forceinline__ void sincos_fast(double x, double* sp, double* cp) {
+  if (!(fabs(x) < 1.0e5)) {
+    sincos_slow(x, sp, cp);
+    return;
+  }
+  const int k = __double2int_rn(x * SC_TAB[0]);
+  const double kd = (double)k;
+  double r = fma(-kd, SC_TAB[1], x);
+  r = fma(-kd, SC_TAB[2], r);
+  r = fma(-kd, SC_TAB[3], r);
+  const double z = r * r;
+  // sin(r) = r + r*z*(S1 + z*(S2 + ... ))
+  double ps = fma(z, SC_TAB[9], SC_TAB[8]);
+  ps = fma(z, ps, SC_TAB[7]);
+  ps = fma(z, ps, SC_TAB[6]);
+  ps = fma(z, ps, SC_TAB[5]);
+  ps = fma(z, ps, SC_TAB[4]);
+  const double s = fma(r * z, ps, r);
+  // cos(r) = 1 + z*(-1/2 + z*(C1 + z*(C2 + ...)))
+  double pc = fma(z, SC_TAB[15], SC_TAB[14]);
+  pc = fma(z, pc, SC_TAB[13]);
+  pc = fma(z, pc, SC_TAB[12]);
+  pc = fma(z, pc, SC_TAB[11]);
+  pc = fma(z, pc, SC_TAB[10]);
+  pc = fma(z, pc, -0.5);
+  const double c = fma(z, pc, 1.0);
+  // quadrant: k mod 4 = 0: (s, c), 1: (c, -s), 2: (-s, -c), 3: (-c, s)
+  const bool swap = (k & 1) != 0;
+  double so = swap ? c : s;
+  double co = swap ? s : c;
+  if (k & 2) so = -so;
+  if ((k + 1) & 2) co = -co;
+  *sp = so;
+  *cp = co;
+}
+
+}  // namespace clik

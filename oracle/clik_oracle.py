@@ -55,16 +55,18 @@ class Block:
 
 def _gain_times(gain, vec):
     """cs.mtimes(gain, vec): scalar * vector or matrix @ vector (constraints.py:36-51)."""
-    g = np.asarray(gain, dtype=np.float64)
+    g = np.asarray(gain, dtype=vec.dtype)
     if g.ndim == 0 or g.size == 1:
-        return float(g.reshape(-1)[0]) * vec
+        return g.reshape(-1)[0] * vec
     if g.ndim == 2:
         return np.einsum("ij,nj->ni", g, vec)
     return np.einsum("nij,nj->ni", g, vec)
 
 
 def _bcast(val, N, m):
-    a = np.asarray(val, dtype=np.float64)
+    a = np.asarray(val)
+    if a.dtype not in (np.float64, np.longdouble):
+        a = a.astype(np.float64)
     if a.ndim == 0:
         a = np.full((m,), float(a))
     if a.ndim == 2 and a.shape[1] == 1 and a.shape[0] == m:
@@ -91,6 +93,31 @@ def activation_map(n_sets: int) -> List[List[int]]:
 # pseudo_inverse.py:92-105  pinv
 # ----------------------------------------------------------------------------------------------
 
+def _solve(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """Batched A X = B.  float64: LAPACK dgesv (partial pivoting).  Any other dtype (the tests use
+    np.longdouble as a higher-precision referee): the same algorithm written out in NumPy."""
+    if A.dtype == np.float64:
+        return np.linalg.solve(A, B)
+    A = A.copy()
+    B = B.copy()
+    N, k, _ = A.shape
+    ar = np.arange(N)
+    for c in range(k):
+        piv = c + np.argmax(np.abs(A[:, c:, c]), axis=1)
+        rows_c, rows_p = A[ar, c].copy(), A[ar, piv].copy()
+        A[ar, c], A[ar, piv] = rows_p, rows_c
+        rows_c, rows_p = B[ar, c].copy(), B[ar, piv].copy()
+        B[ar, c], B[ar, piv] = rows_p, rows_c
+        f = A[:, c + 1:, c] / A[:, c, c][:, None]
+        A[:, c + 1:, :] -= f[:, :, None] * A[:, c, :][:, None, :]
+        B[:, c + 1:, :] -= f[:, :, None] * B[:, c, :][:, None, :]
+    X = np.zeros_like(B)
+    for r in range(k - 1, -1, -1):
+        acc = B[:, r, :] - np.einsum("nk,nkj->nj", A[:, r, r + 1:], X[:, r + 1:, :])
+        X[:, r, :] = acc / A[:, r, r][:, None]
+    return X
+
+
 def damped_pinv(J: np.ndarray, method: str = "damped", damping: float = 1e-7) -> np.ndarray:
     """J: (N, m, n) -> (N, n, m).
     damped:   cols >= rows: (solve(J J' + lam I, J))'   else  solve(J' J + lam I, J')
@@ -107,10 +134,10 @@ def damped_pinv(J: np.ndarray, method: str = "damped", damping: float = 1e-7) ->
     else:
         raise ValueError(method)
     if wide:
-        inner = J @ Jt + lam * np.eye(m)
-        return np.swapaxes(np.linalg.solve(inner, J), -1, -2)
-    inner = Jt @ J + lam * np.eye(n)
-    return np.linalg.solve(inner, Jt)
+        inner = J @ Jt + J.dtype.type(lam) * np.eye(m, dtype=J.dtype)
+        return np.swapaxes(_solve(inner, J), -1, -2)
+    inner = Jt @ J + J.dtype.type(lam) * np.eye(n, dtype=J.dtype)
+    return _solve(inner, Jt)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -136,10 +163,11 @@ def _mode_velocity(blocks: Sequence[Block], active_bits: Sequence[int], n: int, 
     multidim = opts.get("multidim_sets", False)
     if conv_last or multidim:
         raise NotImplementedError("oracle covers the default (non-experimental) options")
-    v = np.zeros((N, n))
+    dt = blocks[0].J.dtype
+    v = np.zeros((N, n), dtype=dt)
     Jlist, rJlist, to_test = [], [], []
     set_idx = 0
-    eye = np.eye(n)
+    eye = np.eye(n, dtype=dt)
 
     def nullspace_term(Ji, des):
         J0 = np.concatenate(Jlist, axis=1)
@@ -186,14 +214,23 @@ def _mode_velocity(blocks: Sequence[Block], active_bits: Sequence[int], n: int, 
     return v, to_test
 
 
+def as_dtype(blocks: Sequence[Block], dtype):
+    """Copy of the numeric blocks in another floating type (np.longdouble = referee precision)."""
+    def c(a):
+        return None if a is None else np.asarray(a, dtype=dtype)
+    return [Block(b.kind, c(b.e), c(b.J), c(b.Jt), c(b.gain), c(b.set_min), c(b.set_max),
+                  c(b.target), b.soft, b.slack_weight) for b in blocks]
+
+
 def pinv_step(blocks: Sequence[Block], n_state: int, options: Optional[dict] = None):
     """PseudoInverseController.solve for N instances.  Returns (v (N, n_state), mode (N,) int32);
-    mode = -1 and v = 0 where no mode is admissible (pseudo_inverse.py:551-555)."""
+    mode = -1 and v = 0 where no mode is admissible (pseudo_inverse.py:551-555).
+    Works in the dtype of the blocks (float64 = the reference's arithmetic)."""
     opts = dict(options or {})
     N = blocks[0].e.shape[0]
     n_sets = sum(1 for b in blocks if b.kind == SET)
     amap = activation_map(n_sets) or [[]]
-    v_out = np.zeros((N, n_state))
+    v_out = np.zeros((N, n_state), dtype=blocks[0].J.dtype)
     mode_out = np.full((N,), -1, dtype=np.int32)
     todo = np.ones((N,), dtype=bool)
     for mode_idx, bits in enumerate(amap):

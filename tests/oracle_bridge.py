@@ -76,8 +76,12 @@ def blocks_from_skill(spec, t, q, x=None, y=None):
     return blocks, n_state
 
 
-def oracle_pinv(spec, inputs, options=None):
+def oracle_pinv(spec, inputs, options=None, dtype=None):
+    """dtype=np.longdouble evaluates the same literal formulas on the same float64 constraint
+    values (e, J, Jt) in extended precision: the referee for ill-conditioned skills."""
     blocks, n = blocks_from_skill(spec, inputs["t"], inputs["q"], inputs.get("x"), inputs.get("y"))
+    if dtype is not None:
+        blocks = orc.as_dtype(blocks, dtype)
     v, mode = orc.pinv_step(blocks, n, options)
     return v.T.copy(), mode
 

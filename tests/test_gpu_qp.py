@@ -1,0 +1,184 @@
+"""Parity of the CUDA reactive-QP path (through the C ABI) with the oracle.
+
+Tolerances (BASELINE.json:north_star): objective and constraint residual within 1e-6; the active
+set must match the oracle's bit for bit.  On top of that every solution is certified with the
+solver-independent KKT residuals (the QP is strictly convex, so KKT <=> the unique optimum that
+qpOASES converges to in the reference)."""
+import numpy as np
+import pytest
+
+from oracle_bridge import orc, oracle_qp_problem
+import casclik_b200 as cc
+from casclik_b200 import cs, scenarios, runtime
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available(), "the gpu tests need a CUDA device"
+    return torch
+
+
+def _solve_device(ctrl, inp, warm=None):
+    torch = _torch()
+    up = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    sol, status, active = ctrl.solve_batch(up(inp["t"]), up(inp["q"]), up(inp.get("x")),
+                                           up(inp.get("y")), warmstart=up(warm))
+    torch.cuda.synchronize()
+    return sol.cpu().numpy(), status.cpu().numpy(), active.cpu().numpy().astype(np.uint32)
+
+
+def _masks(lam):
+    m = lam.shape[1]
+    up = np.zeros(lam.shape[0], dtype=np.uint32)
+    lo = np.zeros(lam.shape[0], dtype=np.uint32)
+    for r in range(min(m, 32)):
+        up |= (lam[:, r] > 0).astype(np.uint32) << np.uint32(r)
+        lo |= (lam[:, r] < 0).astype(np.uint32) << np.uint32(r)
+    return up, lo
+
+
+def _check_against_oracle(spec, ctrl, inp, n_check=None):
+    h, A, lb, ub = oracle_qp_problem(spec, inp)
+    sol, status, active = _solve_device(ctrl, inp)
+    N = A.shape[0]
+    idx = np.arange(N) if n_check is None else np.arange(0, N, max(1, N // n_check))
+    xo, lamo, sto = orc.solve_qp(h, A[idx], lb[idx], ub[idx])
+    assert np.all(sto == 0)
+    assert np.all(status[idx] == runtime.QP_SOLVED)
+    xs = sol[:, idx].T
+    obj = 0.5 * np.sum(h * xs * xs, axis=1)
+    obj_o = 0.5 * np.sum(h * xo * xo, axis=1)
+    assert np.all(np.abs(obj - obj_o) <= TOL * (1 + np.abs(obj_o))), np.abs(obj - obj_o).max()
+    r = np.einsum("nij,nj->ni", A[idx], xs)
+    scale = 1 + np.abs(r)
+    assert np.all(lb[idx] - r <= TOL * scale) and np.all(r - ub[idx] <= TOL * scale)
+    assert np.abs(xs - xo).max() <= 1e-7 * (1 + np.abs(xo).max())
+    up_o, lo_o = _masks(lamo)
+    assert np.array_equal(active[0, idx], up_o), "upper active-set flags differ"
+    assert np.array_equal(active[1, idx], lo_o), "lower active-set flags differ"
+    # solver-independent certificate on every checked instance
+    for k, i in enumerate(idx[:256]):
+        kk = orc.kkt_residuals(h, A[i], lb[i], ub[i], xs[k])
+        assert kk["primal"] < 1e-8 and kk["stationarity"] < 1e-8 and kk["sign"] < 1e-8, kk
+    return sol, status, active
+
+
+def test_ur5_qp_parity_and_kkt():
+    sc = scenarios.get("ur5_qp")
+    ctrl = sc.make_controller()
+    ctrl.setup_problem_functions()
+    ctrl.setup_solver()
+    inp = sc.sample(2048, seed=0)
+    sol, status, active = _check_against_oracle(sc.spec, ctrl, inp)
+    assert (active[0] | active[1]).any(), "some speed limits must be active with K = 50"
+    # host ABI == device ABI, bit for bit
+    sh, sth, ah = ctrl.solve_batch(inp["t"], inp["q"], None, inp["y"])
+    assert np.array_equal(sh, sol) and np.array_equal(sth, status)
+    assert np.array_equal(ah.astype(np.uint32), active)
+    # warm start (primal guess, as the reference's x0=) does not change the answer
+    sw, stw, aw = _solve_device(ctrl, inp, warm=sol)
+    assert np.array_equal(sw, sol) and np.array_equal(aw, active)
+
+
+def test_moe2016_qp_time_varying_parity():
+    sc = scenarios.get("ur5_moe2016_qp")
+    ctrl = sc.make_controller()
+    ctrl.setup_problem_functions()
+    ctrl.setup_solver()
+    _check_against_oracle(sc.spec, ctrl, sc.sample(1024, seed=2))
+
+
+def _cart():
+    t, p, dp = cs.MX.sym("t"), cs.MX.sym("p"), cs.MX.sym("dp")
+    eq = cc.EqualityConstraint("min_dist_cnstr", 0.75 - p, gain=1.0, constraint_type="soft", priority=1)
+    lim = cc.SetConstraint("cart_limit_cnstr", p, gain=1.0, set_min=0.0, set_max=1.0)
+    spd = cc.VelocitySetConstraint("speed_limit_cnstr", p, gain=10.0, set_min=-0.275, set_max=0.275)
+    return cc.SkillSpecification("cart_qp", t, p, robot_vel_var=dp, constraints=[eq, lim, spd])
+
+
+def test_cart_known_answers_through_single_instance_api():
+    ctrl = cc.ReactiveQPController(skill_spec=_cart(), robot_var_weights=[1.0])
+    ctrl.setup_problem_functions()
+    ctrl.setup_solver()
+    rv, vv, sl = ctrl.solve(time_var=0.0, robot_var=0.0)                    # KAT Q1
+    assert vv is None
+    assert abs(float(rv) - 0.275) < 1e-12 and abs(float(sl) - 0.475) < 1e-12
+    assert abs(ctrl.res["cost"] - 0.112963125) < 1e-12
+    assert ctrl.res["active_upper"] == 0b101 and ctrl.res["active_lower"] == 0     # eq row + speed row, both held from above
+    rv, _, sl = ctrl.solve(0.0, 0.6, warmstart_slack_var=[0.475])            # KAT Q2
+    assert abs(float(rv) - 0.14985029940119762) < 1e-12
+    assert abs(float(sl) - 1.4970059880239917e-4) < 1e-12
+    # initial-value problem (robot velocity fixed at 0): slack = 0.75 - p
+    ctrl.setup_initial_problem_solver()
+    virt0, slack0 = ctrl.solve_initial_problem(0.0, 0.25)
+    assert virt0 is None and abs(float(slack0) - 0.5) < 1e-12
+
+
+def test_virtual_variable_qp():
+    t, p, dp = cs.MX.sym("t"), cs.MX.sym("p"), cs.MX.sym("dp")
+    x, dx = cs.MX.sym("x"), cs.MX.sym("dx")
+    up = cc.EqualityConstraint("move_up_path_cnstr", 300 - x, gain=1.0, constraint_type="soft", priority=1)
+    slow = cc.VelocitySetConstraint("slow_path_cnstr", x, set_min=-0.5, set_max=0.5)
+    dist = cc.EqualityConstraint("min_dist_cnstr", 0.4 * cs.sin(0.3 * x) - p, gain=1.0,
+                                 constraint_type="soft", priority=1)
+    lim = cc.SetConstraint("cart_limit_cnstr", p, gain=1.0, set_min=0.0, set_max=1.0)
+    spd = cc.VelocitySetConstraint("speed_limit_cnstr", p, set_min=-0.275, set_max=0.275)
+    spec = cc.SkillSpecification("path_trajectory_skill", t, p, robot_vel_var=dp, virtual_var=x,
+                                 virtual_vel_var=dx, constraints=[up, slow, dist, lim, spd])
+    ctrl = cc.ReactiveQPController(spec, robot_var_weights=[1.0])
+    ctrl.setup_problem_functions()
+    ctrl.setup_solver()
+    rng = np.random.default_rng(1)
+    N = 300
+    inp = {"t": np.zeros(N), "q": rng.uniform(0.0, 1.0, (1, N)), "x": rng.uniform(0, 10, (1, N))}
+    _check_against_oracle(spec, ctrl, inp)
+    rv, vv, sl = ctrl.solve(0.0, 0.3, virtual_var=1.0)
+    assert vv is not None and sl.shape == (2, 1)
+    assert abs(float(vv) - 0.5) < 1e-9      # path variable saturates its speed limit
+
+
+def test_infeasible_and_iteration_cap_are_status_flags():
+    t, p = cs.MX.sym("t"), cs.MX.sym("p")
+    a = cc.VelocitySetConstraint("a", p, set_min=1.0, set_max=2.0)
+    b = cc.VelocitySetConstraint("b", p, set_min=-3.0, set_max=-2.0)
+    spec = cc.SkillSpecification("infeasible", t, p, constraints=[a, b])
+    ctrl = cc.ReactiveQPController(spec)
+    ctrl.setup_problem_functions()
+    ctrl.setup_solver()
+    sol, status, _ = ctrl.solve_batch(np.zeros(3), np.zeros((1, 3)))
+    assert np.all(status == runtime.QP_INFEASIBLE)
+    with pytest.raises(RuntimeError):
+        ctrl.solve(0.0, 0.0)
+    sc = scenarios.get("ur5_qp")
+    c2 = sc.make_controller()
+    c2.setup_problem_functions()
+    inp = sc.sample(64, seed=0)
+    _, st, _ = c2.solve_batch(inp["t"], inp["q"], None, inp["y"], max_iter=1)
+    assert np.all((st == runtime.QP_MAXITER) | (st == runtime.QP_SOLVED)) and (st == runtime.QP_MAXITER).any()
+
+
+def test_conic_object_dense_random_problems():
+    """cs.conic-style call on numeric matrices (clik_qp_dense) vs oracle + KKT, incl. +-inf and
+    +-1e10 default bounds (SetConstraint defaults, reference constraints.py:199-206)."""
+    solver = cs.conic("solver", "qpoases", {}, {})
+    rng = np.random.default_rng(5)
+    N, n, m = 200, 7, 12
+    h = rng.uniform(0.001, 2.0, (N, n))
+    A = rng.normal(size=(N, m, n))
+    r = np.einsum("nij,nj->ni", A, rng.normal(size=(N, n)))
+    lb, ub = r - rng.uniform(0, 1, (N, m)), r + rng.uniform(0, 1, (N, m))
+    lb[:, 0], ub[:, 1] = -np.inf, np.inf
+    lb[:, 2], ub[:, 2] = -1e10, 1e10
+    lb[:, 3] = ub[:, 3] = r[:, 3]
+    x, status, active = solver.solve_dense_batch(h, A, lb, ub)
+    assert np.all(status == 0)
+    for i in range(N):
+        xo, lamo, sto = orc.solve_qp_single(h[i], A[i], lb[i], ub[i])
+        assert sto == 0 and np.abs(x[i] - xo).max() < 1e-8 * (1 + np.abs(xo).max())
+        kk = orc.kkt_residuals(h[i], A[i], lb[i], ub[i], x[i])
+        assert kk["primal"] < 1e-8 and kk["stationarity"] < 1e-8 and kk["sign"] < 1e-8
+    res = solver(h=np.diag(h[0]), a=A[0], lba=lb[0], uba=ub[0])
+    assert np.abs(res["x"].toarray()[:, 0] - x[0]).max() == 0.0
