@@ -150,13 +150,20 @@ class Emitter(object):
 # hand-written-kernel flop model (mode 0 of the static path), mirrors csrc/clik_pinv.cuh
 # ----------------------------------------------------------------------------------------------
 
-def _spd_solve_flops(k):
+def _chol_flops(k):
     f = 0
     for j in range(k):
         f += 2 * j + 2                      # diagonal fma chain + rsqrt (sqrt + div)
         f += (k - j - 1) * (2 * j + 1)      # column below the diagonal
-    f += 2 * sum(2 * i + 1 for i in range(k))   # forward + backward substitution
     return f
+
+
+def _subst_flops(k):
+    return 2 * sum(2 * i + 1 for i in range(k))   # forward + backward substitution
+
+
+def _spd_solve_flops(k):
+    return _chol_flops(k) + _subst_flops(k)
 
 
 def pinv_mode0_flops(prog):
@@ -205,7 +212,14 @@ def pinv_mode0_flops(prog):
                 flops += ns
                 stack = stack + own
                 if b["kind"] == KIND_EQ:
-                    flops += nullspace(stack) + ns
+                    if getattr(prog, "fuse_first_eq", True):
+                        # first_equality_twice: one more substitution on the same factor
+                        k = len(own)
+                        wide = (ns >= k) if prog.damped else (k < ns)
+                        flops += (_subst_flops(k) + 2 * k) if wide else (_subst_flops(ns) + 2 * ns)
+                        flops -= ns          # a single v += w
+                    else:
+                        flops += nullspace(stack) + ns
                     stack = stack + own
             else:
                 flops += nullspace(stack) + ns
@@ -265,6 +279,10 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
                    % (len(pinv.blocks), pinv.m, pinv.n_sets, len(masks), pinv.max_rows))
         out.append("  static constexpr bool DAMPED = %s;" % ("true" if pinv.damped else "false"))
         out.append("  static constexpr double LAMBDA = %s;" % literal(pinv.damping))
+        fuse = os.environ.get("CLIK_FUSE_FIRST_EQ", "1") == "1"
+        pinv.fuse_first_eq = fuse
+        out.append("  static constexpr bool FUSE_FIRST_EQ = %s;" % ("true" if fuse else "false"))
+        meta["fuse_first_eq"] = fuse
         out.append(_switch("kind", kinds))
         out.append(_switch("row0", [b["row0"] for b in pinv.blocks]))
         out.append(_switch("rows", [b["rows"] for b in pinv.blocks]))

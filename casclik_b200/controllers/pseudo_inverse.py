@@ -171,6 +171,8 @@ class PseudoInverseController(BaseController):
               warmstart_slack_var=None):
         """One controller step -> (cntrl_rob, cntrl_virt | None, None); sets `current_mode`."""
         spec = self.skill_spec
+        if getattr(self, "_cubin", None) is None:
+            raise RuntimeError("call setup_problem_functions() / setup_solver() before solve()")
         nq = spec.n_robot_var
         q = as_vector(robot_var, nq, "robot_var").reshape(nq, 1)
         use_virt = virtual_var is not None and spec._has_virtual

