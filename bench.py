@@ -82,6 +82,19 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def _launch_info(ctrl, is_qp):
+    sk = ctrl._skill()
+    if is_qp:
+        return sk.launch_info(1)
+    info = {"plain": sk.launch_info(0)}
+    try:
+        info["tma"] = sk.launch_info(2)
+        info["used"] = "tma" if os.environ.get("CLIK_TMA", "0") == "1" else "plain"
+    except Exception:
+        info["used"] = "plain"
+    return info
+
+
 def cpu_reference(scenario, batch, seconds_target=12.0, threads=0):
     """Restated reference CPU path (oracle/clik_oracle.c) on a bounded sample of the workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -313,7 +326,7 @@ def main():
                        "parallelism": "independent shards, one per GPU, no collective on the data path",
                        "l2": "rotating %d resident input sets (%d MB total) > 126 MB L2"
                              % (args.sets, args.sets * bytes_step * B // (1 << 20)),
-                       "launch": ctrl._skill().launch_info(1 if is_qp else 0)},
+                       "launch": _launch_info(ctrl, is_qp)},
             "roofline": {k: v for k, v in roof.items()},
             "roofline_detail": detail,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),

@@ -40,6 +40,7 @@ class Emitter(object):
         self.hist = {}
         self.const_table = const_table   # list collecting constants that go to the constant bank
         self.sincos_name = sincos_name
+        self.sincos_calls = []           # (line index, argument, sin var, cos var)
 
     def _const(self, v):
         """Constants whose low 32 bits are zero fit an instruction immediate; everything else is
@@ -85,6 +86,9 @@ class Emitter(object):
                 pair = paired[n.args[0].id]
                 s, c = self._tmp(), self._tmp()
                 self.lines.append("double %s, %s; %s(%s, &%s, &%s);" % (s, c, self.sincos_name, a[0], s, c))
+                if self.sincos_name != "sincos":
+                    # deferred range check: patched right after the last fast evaluation
+                    self.sincos_calls.append((len(self.lines) - 1, a[0], s, c))
                 self.name[pair["sin"].id] = s
                 self.name[pair["cos"].id] = c
                 other = pair["cos" if op == "sin" else "sin"]
@@ -134,6 +138,73 @@ class Emitter(object):
         self.roots = getattr(self, "roots", [])
         self.roots.append(node)
         self.lines.append("%s = %s;" % (lhs, self._ref(node)))
+
+    def finish(self):
+        """Emitted statements, with the out-of-range fix-up of the branch-free sincos calls: every
+        run of fast calls whose arguments are available is followed by ONE combined range test,
+        so the compiler is free to interleave the polynomial chains of all joints."""
+        if not self.sincos_calls:
+            return list(self.lines)
+        # group calls whose arguments are inputs/early values: a call can join the current group
+        # only if its argument does not depend on a sin/cos result of the same group; kinematic
+        # chains take sin/cos of the raw joint angles, so in practice there is one group.
+        out = list(self.lines)
+        groups, cur, produced = [], [], set()
+        for idx, arg, sv, cv in self.sincos_calls:
+            if cur and any(p in self._deps_text(arg) for p in produced):
+                groups.append(cur)
+                cur, produced = [], set()
+            cur.append((idx, arg, sv, cv))
+            produced.update((sv, cv))
+        groups.append(cur)
+        import re
+        def_line = {}
+        for i, ln in enumerate(self.lines):
+            if ln.startswith("const double "):
+                def_line[ln[len("const double "):].split(" = ", 1)[0]] = i
+        for g in reversed(groups):
+            first = g[0][0]
+            # lines to hoist to the position of the group's first call: the calls themselves and
+            # every definition after `first` that one of their arguments depends on
+            hoist = set(idx for idx, _, _, _ in g)
+            for _, arg, _, _ in g:
+                for name in self._deps_text(arg):
+                    i = def_line.get(name)
+                    if i is not None and i > first:
+                        hoist.add(i)
+            last = g[-1][0]
+            region = list(range(first, last + 1))
+            moved = [out[i] for i in region if i in hoist]
+            rest = [out[i] for i in region if i not in hoist]
+            test = " && ".join("clik::sincos_in_range(%s)" % arg for _, arg, _, _ in g)
+            fix = ["if (!(%s)) {" % test]
+            for _, arg, sv, cv in g:
+                fix.append("  if (!clik::sincos_in_range(%s)) clik::sincos_slow(%s, &%s, &%s);" % (arg, arg, sv, cv))
+            fix.append("}")
+            out[first:last + 1] = moved + fix + rest
+        return out
+
+    def _deps_text(self, arg):
+        # arguments are temporaries or symbols; a conservative textual dependency walk
+        seen, stack = set(), [arg]
+        defs = getattr(self, "_defs", None)
+        if defs is None:
+            defs = {}
+            for ln in self.lines:
+                if ln.startswith("const double "):
+                    name, rhs = ln[len("const double "):].split(" = ", 1)
+                    defs[name] = rhs
+            self._defs = defs
+        while stack:
+            a = stack.pop()
+            if a in seen:
+                continue
+            seen.add(a)
+            rhs = defs.get(a)
+            if rhs:
+                import re
+                stack.extend(re.findall(r"v\d+", rhs))
+        return seen
 
     def inputs_read(self):
         """Number of distinct input scalars (t, q_i, x_i, y_i) the emitted program reads: loads of
@@ -317,10 +388,41 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
                     em.assign("d.jt[%d]" % gr, b["jt"][r])
                     em.assign("d.smin[%d]" % gr, b["smin"][r])
                     em.assign("d.smax[%d]" % gr, b["smax"][r])
-        body = em.lines
+        body = em.finish()
         out.append("  __device__ static __forceinline__ void eval(%s, clik::PinvData<Skill>& d) {" % sig)
         out += ["    " + ln for ln in body]
         out.append("  }")
+        # rows staged through shared memory by the TMA driver: only the inputs the program reads
+        read_ids = {n.id for n in dag.symbols_of(em.roots)}
+        staged = []          # (array name, row, C lvalue)
+        if pinv.syms.t[0].id in read_ids:
+            staged.append(("t", 0, "tv"))
+        for arr, nodes, lv in (("q", pinv.syms.q, "qv"), ("x", pinv.syms.x, "xv"), ("y", pinv.syms.y, "yv")):
+            for j, n in enumerate(nodes):
+                if n.id in read_ids:
+                    staged.append((arr, j, "%s[%d]" % (lv, j)))
+        t_staged = bool(staged) and staged[0][0] == "t"
+        out.append("  static constexpr int NIN = %d;   // input rows read by eval (t first if read)" % len(staged))
+        out.append("  __device__ static __forceinline__ const double* in_row(int k, long long N, const double* t,")
+        out.append("      const double* q, const double* x, const double* y) {")
+        out.append("    switch (k) {")
+        for k, (arr, j, _) in enumerate(staged):
+            out.append("      case %d: return %s + %dLL * N;" % (k, arr, j) if arr != "t" else
+                       "      case %d: return t;" % k)
+        out.append("      default: return q;")
+        out.append("    }")
+        out.append("  }")
+        out.append("  template <int TILE> __device__ static __forceinline__ void unstage(const double (*b)[TILE], int tid,")
+        out.append("      int t_stride, double& tv, double (&qv)[%d], double (&xv)[%d], double (&yv)[%d]) {"
+                   % (max(nq, 1), max(nxv, 1), max(ny, 1)))
+        for k, (arr, j, lv) in enumerate(staged):
+            if arr == "t":
+                out.append("    if (t_stride != 0) tv = b[%d][tid];" % k)
+            else:
+                out.append("    %s = b[%d][tid];" % (lv, k))
+        out.append("  }")
+        meta["pinv_staged_rows"] = len(staged)
+        meta["pinv_t_read"] = t_staged
         cnt = em.counts()
         meta["pinv_eval"] = cnt
         meta["pinv_algebra_flops_mode0"] = pinv_mode0_flops(pinv)
@@ -342,7 +444,7 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         for j in range(qp.nx):
             em.assign("d.h[%d]" % j, qp.h[j])
         out.append("  __device__ static __forceinline__ void eval_qp(%s, clik::QpData<Skill>& d) {" % sig)
-        out += ["    " + ln for ln in em.lines]
+        out += ["    " + ln for ln in em.finish()]
         out.append("  }")
         meta["qp_eval"] = em.counts()
         meta["qp_inputs_read"] = em.inputs_read()
@@ -359,7 +461,15 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out.append('extern "C" __global__ void %s clik_pinv_kernel(' % bounds)
         out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
         out.append("    const double* y, double* qdot, double* xdot, int* mode) {")
-        out.append("  clik::pinv_step<Skill>(N, t, t_stride, q, x, y, qdot, xdot, mode);")
+        unroll = int(os.environ.get("CLIK_UNROLL", "1"))
+        meta["pinv_unroll"] = unroll
+        out.append("  clik::pinv_step<Skill, %d>(N, t, t_stride, q, x, y, qdot, xdot, mode);" % unroll)
+        out.append("}")
+        out.append('extern "C" __global__ void %s clik_pinv_tma_kernel(' % bounds)
+        out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
+        out.append("    const double* y, double* qdot, double* xdot, int* mode) {")
+        out.append("  clik::pinv_step_tma<Skill, %d, %d>(N, t, t_stride, q, x, y, qdot, xdot, mode);"
+                   % (block_threads, int(os.environ.get("CLIK_STAGES", "2"))))
         out.append("}")
     if qp is not None:
         out.append('extern "C" __global__ void __launch_bounds__(%d) clik_qp_kernel(' % block_threads)
@@ -369,8 +479,8 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out.append("  clik::qp_step<Skill>(N, t, t_stride, q, x, y, x0, sol, status, active, max_iter);")
         out.append("}")
     out.append('extern "C" __global__ void clik_sizes_kernel(int* o) {')
-    out.append("  o[0] = %d; o[1] = %d; o[2] = %d; o[3] = %d; o[4] = %d; o[5] = %d; o[6] = 0; o[7] = 0;"
-               % (nq, nxv, ny, meta["n_modes"], meta["qp_n"], meta["qp_m"]))
+    out.append("  o[0] = %d; o[1] = %d; o[2] = %d; o[3] = %d; o[4] = %d; o[5] = %d; o[6] = %d; o[7] = 0;"
+               % (nq, nxv, ny, meta["n_modes"], meta["qp_n"], meta["qp_m"], meta.get("pinv_unroll", 1)))
     out.append("}")
     return "\n".join(out) + "\n", meta
 
@@ -384,6 +494,6 @@ def emit_c_function(name, sym_names, outputs, arg_decl):
              "static void sincos_(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }",
              "#define sincos sincos_",
              "void %s(%s, double* out) {" % (name, arg_decl)]
-    lines += ["  " + ln for ln in em.lines]
+    lines += ["  " + ln for ln in em.finish()]
     lines.append("}")
     return "\n".join(lines) + "\n"

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <cstdint>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -46,6 +47,8 @@ clik_status fail(clik_status code, const char* fmt, ...) {
 struct KernelInfo {
   cudaKernel_t kernel = nullptr;
   int grid = 0, block = 0, regs = 0, local_bytes = 0;
+  int unroll = 1;    // instances per thread per grid-stride iteration (plain pinv kernel)
+  int resident = 0;  // CTAs that fit on the device at once (SM count x occupancy)
 };
 
 // device scratch for the host-buffer pipeline (two slots, sized on demand)
@@ -60,7 +63,8 @@ struct Scratch {
 struct clik_skill {
   clik_skill_desc desc;
   cudaLibrary_t lib = nullptr;
-  KernelInfo pinv, qp;
+  KernelInfo pinv, pinv_tma, qp;
+  bool use_tma = false;  // opt-in (CLIK_TMA=1): measured slower than the plain kernel, see DESIGN.md
   int sm_count = 0;
   std::mutex mu;  // guards scratch
   Scratch scratch;
@@ -80,6 +84,7 @@ clik_status setup_kernel(clik_skill* s, const char* name, KernelInfo* k) {
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k->kernel, k->block, 0));
   if (per_sm < 1) per_sm = 1;
+  k->resident = s->sm_count * per_sm;
   // grid cap = resident CTAs x waves.  waves = 1 is a persistent grid-stride launch; 0 lifts the
   // cap (one CTA per block_threads instances, hardware CTA scheduler balances the tail).
   int waves = 0;
@@ -89,9 +94,21 @@ clik_status setup_kernel(clik_skill* s, const char* name, KernelInfo* k) {
 }
 
 int grid_for(const KernelInfo& k, int64_t N) {
-  int64_t need = (N + k.block - 1) / k.block;
+  const int64_t per_cta = (int64_t)k.block * k.unroll;
+  int64_t need = (N + per_cta - 1) / per_cta;
   return (int)std::max<int64_t>(1, std::min<int64_t>(need, k.grid));
 }
+
+// Persistent grid for the TMA-staged kernel: the fewest waves that cover all tiles, then the
+// smallest grid that needs exactly that many waves, so every CTA walks the same number of tiles
+// (+-1) and there is no ragged last wave.
+int balanced_grid(const KernelInfo& k, int64_t N) {
+  const int64_t tiles = (N + k.block - 1) / k.block;
+  const int64_t waves = (tiles + k.resident - 1) / k.resident;
+  return (int)std::max<int64_t>(1, (tiles + waves - 1) / waves);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 clik_status check_common(const clik_skill* s, int64_t N, const double* t, const double* q,
                          const double* x, const double* y) {
@@ -255,6 +272,15 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
   }
   clik_status st = CLIK_OK;
   if (desc->has_pinv) st = setup_kernel(s, "clik_pinv_kernel", &s->pinv);
+  if (st == CLIK_OK && desc->has_pinv) {
+    // optional TMA-staged variant (same arguments); absent in images built without it
+    cudaKernel_t probe_tma;
+    if (cudaLibraryGetKernel(&probe_tma, s->lib, "clik_pinv_tma_kernel") == cudaSuccess)
+      st = setup_kernel(s, "clik_pinv_tma_kernel", &s->pinv_tma);
+    else
+      cudaGetLastError();
+    if (const char* e = getenv("CLIK_TMA")) s->use_tma = atoi(e) != 0;
+  }
   if (st == CLIK_OK && desc->has_qp) st = setup_kernel(s, "clik_qp_kernel", &s->qp);
   // the image carries its own sizes: refuse a descriptor that disagrees
   if (st == CLIK_OK) {
@@ -269,7 +295,7 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
         cudaFree(dsz);
         if (le != cudaSuccess) {
           st = fail(CLIK_ERR_CUDA, "size probe failed: %s", cudaGetErrorString(le));
-        } else if (hsz[0] != desc->n_robot || hsz[1] != desc->n_virtual || hsz[2] != desc->n_input ||
+        } else if ((s->pinv.unroll = hsz[6] > 0 ? hsz[6] : 1), hsz[0] != desc->n_robot || hsz[1] != desc->n_virtual || hsz[2] != desc->n_input ||
                    hsz[3] != desc->n_modes || hsz[4] != desc->qp_n || hsz[5] != desc->qp_m) {
           st = fail(CLIK_ERR_IMAGE,
                     "descriptor does not match cubin: image (n_robot %d, n_virtual %d, n_input %d, "
@@ -304,7 +330,7 @@ void clik_skill_free(clik_skill* s) {
 clik_status clik_skill_launch_info(const clik_skill* s, int32_t which, int32_t* grid, int32_t* block,
                                    int32_t* regs, int32_t* local_bytes) {
   if (!s) return fail(CLIK_ERR_INVALID, "skill is NULL");
-  const KernelInfo& k = which == 0 ? s->pinv : s->qp;
+  const KernelInfo& k = which == 0 ? s->pinv : (which == 2 ? s->pinv_tma : s->qp);
   if (!k.kernel) return fail(CLIK_ERR_INVALID, "skill has no such kernel");
   if (grid) *grid = k.grid;
   if (block) *block = k.block;
@@ -325,8 +351,16 @@ clik_status clik_pinv_step(const clik_skill* s, int64_t N, const double* t, int3
   long long n = N;
   int ts = t_stride ? 1 : 0;
   void* args[] = {&n, &t, &ts, &q, &x, &y, &qdot, &xdot, &mode};
-  CK(cudaLaunchKernel((const void*)s->pinv.kernel, dim3(grid_for(s->pinv, N)), dim3(s->pinv.block),
-                      args, 0, (cudaStream_t)stream));
+  // bulk async copies need 16-byte aligned row segments: even N and aligned bases
+  const bool tma_ok = s->use_tma && s->pinv_tma.kernel && (N % 2 == 0) && aligned16(t) && aligned16(q) &&
+                      aligned16(x) && aligned16(y);
+  if (tma_ok) {
+    CK(cudaLaunchKernel((const void*)s->pinv_tma.kernel, dim3(balanced_grid(s->pinv_tma, N)),
+                        dim3(s->pinv_tma.block), args, 0, (cudaStream_t)stream));
+  } else {
+    CK(cudaLaunchKernel((const void*)s->pinv.kernel, dim3(grid_for(s->pinv, N)), dim3(s->pinv.block),
+                        args, 0, (cudaStream_t)stream));
+  }
   return CLIK_OK;
 }
 

@@ -37,11 +37,12 @@ __constant__ double SC_TAB[20] = {
 // arguments outside the fast-reduction range (huge, inf, nan): library routine, kept out of line
 __device__ __noinline__ void sincos_slow(double x, double* sp, double* cp) { sincos(x, sp, cp); }
 
+// Fast path only, no range check: the generated code evaluates all joint angles with this
+// branch-free routine first (so the independent polynomial chains interleave), then tests all
+// arguments at once with sincos_in_range() and re-does the rare out-of-range ones out of line.
+__device__ __forceinline__ bool sincos_in_range(double x) { return fabs(x) < 1.0e5; }
+
 __device__ __forceinline__ void sincos_fast(double x, double* sp, double* cp) {
-  if (!(fabs(x) < 1.0e5)) {
-    sincos_slow(x, sp, cp);
-    return;
-  }
   const int k = __double2int_rn(x * SC_TAB[0]);
   const double kd = (double)k;
   double r = fma(-kd, SC_TAB[1], x);

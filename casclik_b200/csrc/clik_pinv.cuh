@@ -481,51 +481,188 @@ __device__ __noinline__ bool dynamic_mode(const PinvData<S>* d, unsigned mask, d
 }
 
 // ---- the step --------------------------------------------------------------------------------------
-// Structure-of-arrays batch: q[j*N + i] is coordinate j of instance i (same for x, y, outputs), so
-// consecutive threads touch consecutive addresses.  t has stride t_stride (0 = one shared time).
-// mode[i] = index into the activation map of the accepted mode, -1 (and zero velocity) if none.
+// One instance, inputs already in registers: evaluate the skill, try mode 0 on the static path,
+// fall back to the run-time mode search, and return the accepted mode index (-1: none).
 template <class S>
+__device__ __forceinline__ int solve_instance(const double tv, const double (&qv)[Max<S::NQ, 1>::v],
+                                              const double (&xv)[Max<S::NX, 1>::v],
+                                              const double (&yv)[Max<S::NY, 1>::v], double (&v)[S::NS]) {
+  PinvData<S> d;
+  S::eval(tv, qv, xv, yv, d);
+  int accepted = 0;
+  bool ok = static_mode<S, 0u>(d, v);
+  if constexpr (S::NSETS > 0) {
+    if (!ok) {
+      accepted = -1;
+      PinvData<S> copy = d;     // the slow path indexes dynamically: keep `d` itself in registers
+      double vd[S::NS];
+      for (int mi = 1; mi < S::NMODES; ++mi) {
+        if (dynamic_mode<S>(&copy, S::mode_mask(mi), vd)) {
+          accepted = mi;
+          break;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < S::NS; ++j) v[j] = (accepted < 0) ? 0.0 : vd[j];
+    }
+  }
+  return accepted;
+}
+
+template <class S>
+__device__ __forceinline__ void store_instance(long long N, long long i, const double (&v)[S::NS],
+                                               int accepted, double* __restrict__ qdot,
+                                               double* __restrict__ xdot, int* __restrict__ mode) {
+#pragma unroll
+  for (int j = 0; j < S::NQ; ++j) __stcs(qdot + (long long)j * N + i, v[j]);
+#pragma unroll
+  for (int j = 0; j < S::NX; ++j) __stcs(xdot + (long long)j * N + i, v[S::NQ + j]);
+  if (mode != nullptr) __stcs(mode + i, accepted);
+}
+
+// Plain driver.  Structure-of-arrays batch: q[j*N + i] is coordinate j of instance i (same for
+// x, y, outputs), so consecutive threads touch consecutive addresses.  t has stride t_stride
+// (0 = one shared time).  mode[i] = index into the activation map of the accepted mode, -1 (and
+// zero velocity) if none.  Used when the TMA driver's alignment conditions do not hold.
+template <class S>
+__device__ __forceinline__ void load_instance(long long N, long long i, const double* __restrict__ t,
+                                              int t_stride, const double* __restrict__ q,
+                                              const double* __restrict__ x, const double* __restrict__ y,
+                                              double& tv, double (&qv)[Max<S::NQ, 1>::v],
+                                              double (&xv)[Max<S::NX, 1>::v], double (&yv)[Max<S::NY, 1>::v]) {
+  tv = __ldcs(t + (long long)t_stride * i);
+#pragma unroll
+  for (int j = 0; j < S::NQ; ++j) qv[j] = __ldcs(q + (long long)j * N + i);
+#pragma unroll
+  for (int j = 0; j < S::NX; ++j) xv[j] = __ldcs(x + (long long)j * N + i);
+#pragma unroll
+  for (int j = 0; j < S::NY; ++j) yv[j] = __ldcs(y + (long long)j * N + i);
+}
+
+// UNROLL instances per thread: the loads of all of them are issued before the first solve, so
+// the memory latency of instance k+1 hides behind the arithmetic of instance k.
+template <class S, int UNROLL>
 __device__ __forceinline__ void pinv_step(long long N, const double* __restrict__ t, int t_stride,
                                           const double* __restrict__ q, const double* __restrict__ x,
                                           const double* __restrict__ y, double* __restrict__ qdot,
                                           double* __restrict__ xdot, int* __restrict__ mode) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-    double qv[Max<S::NQ, 1>::v], xv[Max<S::NX, 1>::v], yv[Max<S::NY, 1>::v];
-    const double tv = __ldcs(t + (long long)t_stride * i);
+  const long long stride = (long long)gridDim.x * blockDim.x * UNROLL;
+  for (long long base = (long long)blockIdx.x * blockDim.x * UNROLL + threadIdx.x; base < N; base += stride) {
+    double tv[UNROLL], qv[UNROLL][Max<S::NQ, 1>::v], xv[UNROLL][Max<S::NX, 1>::v], yv[UNROLL][Max<S::NY, 1>::v];
 #pragma unroll
-    for (int j = 0; j < S::NQ; ++j) qv[j] = __ldcs(q + (long long)j * N + i);
-#pragma unroll
-    for (int j = 0; j < S::NX; ++j) xv[j] = __ldcs(x + (long long)j * N + i);
-#pragma unroll
-    for (int j = 0; j < S::NY; ++j) yv[j] = __ldcs(y + (long long)j * N + i);
-
-    PinvData<S> d;
-    S::eval(tv, qv, xv, yv, d);
-
-    double v[S::NS];
-    int accepted = 0;
-    bool ok = static_mode<S, 0u>(d, v);
-    if constexpr (S::NSETS > 0) {
-      if (!ok) {
-        accepted = -1;
-        PinvData<S> copy = d;     // the slow path indexes dynamically: keep `d` itself in registers
-        double vd[S::NS];
-        for (int mi = 1; mi < S::NMODES; ++mi) {
-          if (dynamic_mode<S>(&copy, S::mode_mask(mi), vd)) {
-            accepted = mi;
-            break;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < S::NS; ++j) v[j] = (accepted < 0) ? 0.0 : vd[j];
-      }
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long i = base + (long long)u * blockDim.x;
+      if (i < N) load_instance<S>(N, i, t, t_stride, q, x, y, tv[u], qv[u], xv[u], yv[u]);
     }
 #pragma unroll
-    for (int j = 0; j < S::NQ; ++j) __stcs(qdot + (long long)j * N + i, v[j]);
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long i = base + (long long)u * blockDim.x;
+      if (i < N) {
+        double v[S::NS];
+        const int accepted = solve_instance<S>(tv[u], qv[u], xv[u], yv[u], v);
+        store_instance<S>(N, i, v, accepted, qdot, xdot, mode);
+      }
+    }
+  }
+}
+
+// ---- TMA-staged persistent driver -------------------------------------------------------------------
+// One CTA per resident slot walks tiles of TILE = blockDim.x instances.  The input rows the skill
+// actually reads (S::NIN of them; unused coordinates are never fetched) are brought into shared
+// memory with 1-D bulk async copies (cp.async.bulk, the TMA engine) that complete on an mbarrier,
+// STAGES tiles ahead of the arithmetic, so HBM reads run continuously underneath the fp64 work
+// instead of every warp stalling on its own loads first.  Requirements checked by the host
+// (csrc/clik_abi.cu): N even and 16-byte aligned base pointers, so every row segment of a tile is
+// a legal bulk copy (16-byte aligned, size a multiple of 16).
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "CLIK_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra CLIK_DONE;\n"
+      "bra CLIK_WAIT;\n"
+      "CLIK_DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <class S, int TILE, int STAGES>
+__device__ __forceinline__ void pinv_step_tma(long long N, const double* __restrict__ t, int t_stride,
+                                              const double* __restrict__ q, const double* __restrict__ x,
+                                              const double* __restrict__ y, double* __restrict__ qdot,
+                                              double* __restrict__ xdot, int* __restrict__ mode) {
+  constexpr int NIN = S::NIN;
+  __shared__ __align__(128) double buf[STAGES][Max<NIN, 1>::v][TILE];
+  __shared__ __align__(8) unsigned long long full[STAGES];
+  const int tid = threadIdx.x;
+  const long long ntiles = (N + TILE - 1) / TILE;
+
+  auto issue = [&](long long tile, int s) {
+    const long long i0 = tile * TILE;
+    const unsigned cnt = (unsigned)((N - i0 < TILE) ? (N - i0) : TILE);
+    const unsigned bytes = cnt * 8u;
+    mbar_expect_tx(&full[s], bytes * (unsigned)NIN);
 #pragma unroll
-    for (int j = 0; j < S::NX; ++j) __stcs(xdot + (long long)j * N + i, v[S::NQ + j]);
-    if (mode != nullptr) __stcs(mode + i, accepted);
+    for (int k = 0; k < NIN; ++k) bulk_load(&buf[s][k][0], S::in_row(k, N, t, q, x, y) + i0, bytes, &full[s]);
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0 && NIN > 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      const long long tile = (long long)blockIdx.x + (long long)s * gridDim.x;
+      if (tile < ntiles) issue(tile, s);
+    }
+  }
+  const double t_shared = (t_stride == 0) ? __ldg(t) : 0.0;
+  int s = 0;
+  unsigned parity = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long i = tile * TILE + tid;
+    double qv[Max<S::NQ, 1>::v], xv[Max<S::NX, 1>::v], yv[Max<S::NY, 1>::v];
+    double tv = t_shared;
+    if constexpr (NIN > 0) {
+      mbar_wait(&full[s], parity);
+      S::unstage(buf[s], tid, t_stride, tv, qv, xv, yv);
+      __syncthreads();                       // every thread has its inputs in registers
+      if (tid == 0) {
+        const long long nt = tile + (long long)STAGES * gridDim.x;
+        if (nt < ntiles) issue(nt, s);       // refill this stage STAGES tiles ahead
+      }
+    }
+    if (i < N) {
+      double v[S::NS];
+      const int accepted = solve_instance<S>(tv, qv, xv, yv, v);
+      store_instance<S>(N, i, v, accepted, qdot, xdot, mode);
+    }
+    if (++s == STAGES) {
+      s = 0;
+      parity ^= 1u;
+    }
   }
 }
 

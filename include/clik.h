@@ -113,7 +113,7 @@ clik_status clik_qp_step_host(const clik_skill* skill, int64_t N, const double* 
                               double* sol, int32_t* status, uint32_t* active, int32_t max_iter);
 
 /* Launch geometry chosen at load time (for reporting). */
-clik_status clik_skill_launch_info(const clik_skill* skill, int32_t which /*0 pinv, 1 qp*/,
+clik_status clik_skill_launch_info(const clik_skill* skill, int32_t which /*0 pinv, 1 qp, 2 pinv TMA-staged*/,
                                    int32_t* grid, int32_t* block, int32_t* regs_per_thread,
                                    int32_t* local_bytes_per_thread);
 

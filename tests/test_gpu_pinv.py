@@ -199,12 +199,13 @@ def test_full_size_properties_ur5_track():
     ids_q = [s.id for s in sc.spec.robot_var.nodes()]
     ids_y = [s.id for s in sc.spec.input_var.nodes()]
 
+    sub = slice(0, 20000)
+
     def err(qq):
         vals = {i: qq[k] for k, i in enumerate(ids_q)}
-        vals.update({i: inp["y"][k] for k, i in enumerate(ids_y)})
+        vals.update({i: inp["y"][k, sub] for k, i in enumerate(ids_y)})
         e = np.stack(dag.evaluate(nodes, vals))
         return np.sqrt((e * e).sum(axis=0))
-    sub = slice(0, 20000)
     e0 = err(inp["q"][:, sub])
     e1 = err(inp["q"][:, sub] + 1e-3 * v[:, sub].cpu().numpy())
     assert (e1 < e0).mean() > 0.999
@@ -213,6 +214,40 @@ def test_full_size_properties_ur5_track():
     ref_v, _ = oracle_pinv(sc.spec, {"t": inp["t"][idx], "q": inp["q"][:, idx], "y": inp["y"][:, idx]})
     got = v[:, torch.from_numpy(idx).cuda()].cpu().numpy()
     assert close(got, ref_v, RTOL, ATOL).all(), _report(got, ref_v, "ur5_track 2^20 subsample")
+
+
+def test_huge_and_odd_inputs_take_the_fallback_paths():
+    """Angles beyond the fast range reduction (|q| >= 1e5) go through the library sincos; an odd
+    batch size cannot use 16-byte bulk copies and runs the plain kernel.  Same answers."""
+    sc, ctrl = _setup("ur5_track")
+    inp = sc.sample(1001, seed=9)                      # odd N: plain kernel
+    inp["q"][0, ::7] += 2 * np.pi * 40000              # |q| ~ 2.5e5
+    inp["q"][3, ::11] -= 2 * np.pi * 123456
+    ref_v, _ = oracle_pinv(sc.spec, inp)
+    v, _, _ = _run_device(ctrl, inp)
+    assert close(v, ref_v, RTOL, ATOL).all(), _report(v, ref_v, "huge angles, odd N")
+    inp2 = {k: (a[..., :1000] if a is not None else None) for k, a in inp.items()}
+    v2, _, _ = _run_device(ctrl, inp2)
+    assert np.array_equal(v2, v[:, :1000])
+    # the opt-in TMA-staged persistent kernel (bulk async copies + mbarrier ring) gives the same bits
+    import os
+    os.environ["CLIK_TMA"] = "1"
+    try:
+        _, ctrl_tma = _setup("ur5_track")
+        v3, _, m3 = _run_device(ctrl_tma, inp2)          # even N, aligned: TMA path
+        v4, _, _ = _run_device(ctrl_tma, inp)            # odd N: falls back to the plain kernel
+    finally:
+        del os.environ["CLIK_TMA"]
+    assert np.array_equal(v3, v2) and np.array_equal(v4, v) and np.all(m3 == 0)
+    big = sc.sample(300000, seed=4)                      # many tiles per CTA: exercises the stage ring
+    os.environ["CLIK_TMA"] = "1"
+    try:
+        _, ctrl_tma = _setup("ur5_track")
+        vb, _, _ = _run_device(ctrl_tma, big)
+    finally:
+        del os.environ["CLIK_TMA"]
+    vp, _, _ = _run_device(ctrl, big)
+    assert np.array_equal(vb, vp)
 
 
 def test_damping_option_is_read_at_setup_time():
