@@ -465,6 +465,13 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         meta["pinv_unroll"] = unroll
         out.append("  clik::pinv_step<Skill, %d>(N, t, t_stride, q, x, y, qdot, xdot, mode);" % unroll)
         out.append("}")
+        out.append('extern "C" __global__ void %s clik_pinv_rollout_kernel(' % bounds)
+        out.append("    long long N, int steps, double dt, const double* t0, int t_stride, double* q, double* x,")
+        out.append("    const double* y, double vmax_q, double vmax_x, double* qdot_last, double* xdot_last,")
+        out.append("    int* mode_last, int* n_failed) {")
+        out.append("  clik::pinv_rollout<Skill>(N, steps, dt, t0, t_stride, q, x, y, vmax_q, vmax_x, qdot_last,")
+        out.append("                            xdot_last, mode_last, n_failed);")
+        out.append("}")
         out.append('extern "C" __global__ void %s clik_pinv_tma_kernel(' % bounds)
         out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
         out.append("    const double* y, double* qdot, double* xdot, int* mode) {")

@@ -166,6 +166,32 @@ class PseudoInverseController(BaseController):
                                                   b.yp, b.ptr(qdot), b.ptr(xdot), b.ptr(mode)))
         return qdot, xdot, mode
 
+    def rollout_batch(self, time_var0, robot_var, steps, dt, virtual_var=None, input_var=None,
+                      max_speed=None, max_virtual_speed=None):
+        """Closed-loop simulation on the device: `steps` times
+        v = solve(t0 + k*dt, q, x, y); v = clip(v, +-max_speed); q += v_rob*dt; x += v_virt*dt
+        (the loop of the reference notebooks around solve()).  robot_var / virtual_var are torch
+        CUDA tensors (n, N) and are UPDATED IN PLACE.  Returns a dict with the last command
+        (`robot_vel`, `virtual_vel`), its `mode`, and `n_failed` (steps with no admissible mode)."""
+        import ctypes
+        skill = self._skill()
+        spec = self.skill_spec
+        nq, nx, ny = spec.n_robot_var, self._nx, self._ny
+        b = Batch(nq, nx, ny, time_var0, robot_var, virtual_var, input_var if ny else None)
+        if not b.on_device:
+            raise ValueError("rollout_batch needs CUDA tensors (state is updated in place on the device)")
+        if nx and virtual_var is None:
+            raise ValueError("the skill has a virtual_var: pass its initial value")
+        qdot, xdot = b.empty(nq), (b.empty(nx) if nx else None)
+        mode, failed = b.empty(0, "i32"), b.empty(0, "i32")
+        inf = float("inf")
+        runtime.check(runtime.load_library().clik_pinv_rollout(
+            skill.handle, b.N, int(steps), ctypes.c_double(float(dt)), b.tp, b.t_stride, b.qp, b.xp, b.yp,
+            ctypes.c_double(inf if max_speed is None else float(max_speed)),
+            ctypes.c_double(inf if max_virtual_speed is None else float(max_virtual_speed)),
+            b.ptr(qdot), b.ptr(xdot), b.ptr(mode), b.ptr(failed), b.stream()))
+        return {"robot_vel": qdot, "virtual_vel": xdot, "mode": mode, "n_failed": failed}
+
     def solve(self, time_var, robot_var, virtual_var=None, input_var=None,
               warmstart_robot_vel_var=None, warmstart_virtual_vel_var=None,
               warmstart_slack_var=None):

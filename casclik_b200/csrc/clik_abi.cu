@@ -63,7 +63,7 @@ struct Scratch {
 struct clik_skill {
   clik_skill_desc desc;
   cudaLibrary_t lib = nullptr;
-  KernelInfo pinv, pinv_tma, qp;
+  KernelInfo pinv, pinv_tma, pinv_rollout, qp;
   bool use_tma = false;  // opt-in (CLIK_TMA=1): measured slower than the plain kernel, see DESIGN.md
   int sm_count = 0;
   std::mutex mu;  // guards scratch
@@ -280,6 +280,11 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
     else
       cudaGetLastError();
     if (const char* e = getenv("CLIK_TMA")) s->use_tma = atoi(e) != 0;
+    cudaKernel_t probe_ro;
+    if (st == CLIK_OK && cudaLibraryGetKernel(&probe_ro, s->lib, "clik_pinv_rollout_kernel") == cudaSuccess)
+      st = setup_kernel(s, "clik_pinv_rollout_kernel", &s->pinv_rollout);
+    else
+      cudaGetLastError();
   }
   if (st == CLIK_OK && desc->has_qp) st = setup_kernel(s, "clik_qp_kernel", &s->qp);
   // the image carries its own sizes: refuse a descriptor that disagrees
@@ -361,6 +366,24 @@ clik_status clik_pinv_step(const clik_skill* s, int64_t N, const double* t, int3
     CK(cudaLaunchKernel((const void*)s->pinv.kernel, dim3(grid_for(s->pinv, N)), dim3(s->pinv.block),
                         args, 0, (cudaStream_t)stream));
   }
+  return CLIK_OK;
+}
+
+clik_status clik_pinv_rollout(const clik_skill* s, int64_t N, int32_t steps, double dt, const double* t0,
+                              int32_t t_stride, double* q, double* x, const double* y,
+                              double max_robot_speed, double max_virtual_speed, double* qdot_last,
+                              double* xdot_last, int32_t* mode_last, int32_t* n_failed, void* stream) {
+  clik_status st = check_common(s, N, t0, q, x, y);
+  if (st != CLIK_OK || N == 0) return st;
+  if (!s->pinv_rollout.kernel) return fail(CLIK_ERR_INVALID, "skill was built without the rollout kernel");
+  if (steps < 0) return fail(CLIK_ERR_INVALID, "steps < 0");
+  CK(cudaSetDevice(s->desc.device));
+  long long n = N;
+  int ts = t_stride ? 1 : 0, k = steps;
+  void* args[] = {&n, &k, &dt, &t0, &ts, &q, &x, &y, &max_robot_speed, &max_virtual_speed,
+                  &qdot_last, &xdot_last, &mode_last, &n_failed};
+  CK(cudaLaunchKernel((const void*)s->pinv_rollout.kernel, dim3(grid_for(s->pinv_rollout, N)),
+                      dim3(s->pinv_rollout.block), args, 0, (cudaStream_t)stream));
   return CLIK_OK;
 }
 

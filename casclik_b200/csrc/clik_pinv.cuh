@@ -566,6 +566,55 @@ __device__ __forceinline__ void pinv_step(long long N, const double* __restrict_
   }
 }
 
+// ---- closed-loop rollout -------------------------------------------------------------------------------
+// The loop every CASCLIK user runs around solve() (examples/notebooks/ur5_moe2016_example2.ipynb cell 12,
+// lines :535-549): res = solve(t_k, q_k); dq = clip(res, +-max_speed); q_{k+1} = q_k + dq*dt, with
+// t_k = t0 + k*dt, here for `steps` steps per instance without leaving the GPU.  The state update
+// is rounded like the notebook's NumPy code (separate multiply and add, no fma contraction).
+template <class S>
+__device__ __forceinline__ void pinv_rollout(long long N, int steps, double dt, const double* __restrict__ t0,
+                                             int t_stride, double* __restrict__ q, double* __restrict__ x,
+                                             const double* __restrict__ y, double vmax_q, double vmax_x,
+                                             double* __restrict__ qdot_last, double* __restrict__ xdot_last,
+                                             int* __restrict__ mode_last, int* __restrict__ n_failed) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    double t0v, qv[Max<S::NQ, 1>::v], xv[Max<S::NX, 1>::v], yv[Max<S::NY, 1>::v];
+    load_instance<S>(N, i, t0, t_stride, q, x, y, t0v, qv, xv, yv);
+    double v[S::NS];
+#pragma unroll
+    for (int j = 0; j < S::NS; ++j) v[j] = 0.0;
+    int accepted = 0, failed = 0;
+    for (int k = 0; k < steps; ++k) {
+      const double tv = __dadd_rn(t0v, __dmul_rn(dt, (double)k));
+      accepted = solve_instance<S>(tv, qv, xv, yv, v);
+      failed += (accepted < 0) ? 1 : 0;
+#pragma unroll
+      for (int j = 0; j < S::NQ; ++j) {
+        v[j] = fmax(fmin(v[j], vmax_q), -vmax_q);
+        qv[j] = __dadd_rn(qv[j], __dmul_rn(v[j], dt));
+      }
+#pragma unroll
+      for (int j = 0; j < S::NX; ++j) {
+        v[S::NQ + j] = fmax(fmin(v[S::NQ + j], vmax_x), -vmax_x);
+        xv[j] = __dadd_rn(xv[j], __dmul_rn(v[S::NQ + j], dt));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < S::NQ; ++j) {
+      q[(long long)j * N + i] = qv[j];
+      if (qdot_last != nullptr) qdot_last[(long long)j * N + i] = v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < S::NX; ++j) {
+      x[(long long)j * N + i] = xv[j];
+      if (xdot_last != nullptr) xdot_last[(long long)j * N + i] = v[S::NQ + j];
+    }
+    if (mode_last != nullptr) mode_last[i] = accepted;
+    if (n_failed != nullptr) n_failed[i] = failed;
+  }
+}
+
 // ---- TMA-staged persistent driver -------------------------------------------------------------------
 // One CTA per resident slot walks tiles of TILE = blockDim.x instances.  The input rows the skill
 // actually reads (S::NIN of them; unused coordinates are never fetched) are brought into shared

@@ -83,6 +83,19 @@ clik_status clik_pinv_step(const clik_skill* skill, int64_t N, const double* t, 
                            const double* q, const double* x, const double* y, double* qdot,
                            double* xdot, int32_t* mode, void* stream);
 
+/* The simulation loop CASCLIK users run around solve() (examples/notebooks/ur5_moe2016_example2.ipynb
+ * cell 12, raw lines :535-549), `steps` controller steps per instance on the device:
+ *     v = solve(t0 + k*dt, q, x, y);  v = clip(v, +-max_speed);  q += v_rob*dt;  x += v_virt*dt
+ *   q, x            in/out: state at t0 on entry, state after `steps` steps on return
+ *   max_robot_speed, max_virtual_speed   clip limits (pass INFINITY for none)
+ *   qdot_last, xdot_last, mode_last      out, may be NULL: the last (clipped) command and its mode
+ *   n_failed        out, may be NULL: number of steps in which no mode was admissible */
+clik_status clik_pinv_rollout(const clik_skill* skill, int64_t N, int32_t steps, double dt,
+                              const double* t0, int32_t t_stride, double* q, double* x,
+                              const double* y, double max_robot_speed, double max_virtual_speed,
+                              double* qdot_last, double* xdot_last, int32_t* mode_last,
+                              int32_t* n_failed, void* stream);
+
 /* ReactiveQPController.solve (reactive_qp.py:461-528) for N instances.
  *   x0     [qp_n * N] primal warm start or NULL (as the reference's x0=, :495-513)
  *   sol    [qp_n * N] out: [robot vel; virtual vel; slack]

@@ -47,7 +47,12 @@ def chain_table(chain):
 
 
 def max_threads():
-    return int(load().clik_ref_max_threads())
+    """All host cores this process may use.  Deliberately not omp_get_max_threads(): torchrun
+    exports OMP_NUM_THREADS=1, which would silently turn the CPU baseline into a 1-core run."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def pinv_track(chain, q, y, gain=1.0, lam=1e-7, threads=0):

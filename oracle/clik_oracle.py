@@ -340,12 +340,14 @@ def solve_qp_single(hdiag, A, lb, ub, max_iter=200, tol=1e-12):
     W: List[int] = []                        # working set (row indices)
     sg: List[float] = []                     # +1 upper, -1 lower
     u = np.zeros(0)
-    scale = 1.0 + np.max(np.abs(np.where(np.isfinite(lb), lb, 0.0))) + \
-        np.max(np.abs(np.where(np.isfinite(ub), ub, 0.0)))
+    # a row counts as violated beyond 1e-12 * max(1, |its own bound|): the default +-1e10 bounds of a
+    # SetConstraint (constraints.py:199-206) must not loosen the test for the other rows
+    tol_u = tol * np.maximum(1.0, np.abs(np.where(np.isfinite(ub), ub, 1.0)))
+    tol_l = tol * np.maximum(1.0, np.abs(np.where(np.isfinite(lb), lb, 1.0)))
     for _ in range(max_iter):
         r = At @ z
-        viol_u = r - ub
-        viol_l = lb - r
+        viol_u = np.where(r - ub > tol_u, r - ub, -np.inf)
+        viol_l = np.where(lb - r > tol_l, lb - r, -np.inf)
         viol_u[W] = -np.inf
         viol_l[W] = -np.inf
         iu, il = int(np.argmax(viol_u)), int(np.argmax(viol_l))
@@ -353,7 +355,7 @@ def solve_qp_single(hdiag, A, lb, ub, max_iter=200, tol=1e-12):
             p, sp, vp = iu, 1.0, viol_u[iu]
         else:
             p, sp, vp = il, -1.0, viol_l[il]
-        if vp <= tol * scale:
+        if not np.isfinite(vp):
             lam = np.zeros(m)
             for j, (w, g) in enumerate(zip(W, sg)):
                 lam[w] = g * u[j]

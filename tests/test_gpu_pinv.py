@@ -266,3 +266,63 @@ def test_damping_option_is_read_at_setup_time():
     ref_s, _ = oracle_pinv(sc.spec, inp, {"pinv_method": "standard"})
     v2, _, _ = _run_device(ctrl2, inp)
     assert close(v2, ref_s, 1e-8, ATOL).all(), _report(v2, ref_s, "standard pinv")
+
+
+def test_rollout_on_device_matches_stepwise_loop():
+    """K closed-loop steps on the device == K calls of solve_batch with the notebook's
+    clip + Euler update in between (bit for bit: same kernel arithmetic, same update rounding),
+    and the whole trajectory stays within tolerance of the oracle-driven loop."""
+    torch = _torch()
+    sc, ctrl = _setup("ur5_moe2016_pinv")
+    N, K, dt, vmax = 256, 40, 0.008, np.pi / 5
+    inp = sc.sample(N, seed=3)
+    t0 = torch.from_numpy(inp["t"]).cuda()
+    q_dev = torch.from_numpy(inp["q"]).cuda()
+    q_roll = q_dev.clone()
+    out = ctrl.rollout_batch(t0, q_roll, K, dt, max_speed=vmax)
+    q_loop = q_dev.clone()
+    q_orc = inp["q"].copy()
+    modes_equal = np.ones(N, dtype=bool)
+    for k in range(K):
+        tk = t0 + dt * k
+        v, _, mode = ctrl.solve_batch(tk, q_loop)
+        v = torch.clamp(v, -vmax, vmax)
+        q_loop = q_loop + v * dt
+        vo, mo = oracle_pinv(sc.spec, {"t": inp["t"] + dt * k, "q": q_orc})
+        modes_equal &= (mo == mode.cpu().numpy()) | ~modes_equal
+        modes_equal &= (mo == mode.cpu().numpy())
+        q_orc = q_orc + np.clip(vo, -vmax, vmax) * dt
+    torch.cuda.synchronize()
+    assert torch.equal(q_roll, q_loop)
+    assert torch.equal(out["mode"], mode) and torch.equal(out["robot_vel"], v)
+    assert int(out["n_failed"].sum()) == 0
+    # instances whose mode sequence agrees with the oracle's must track it closely; a mode flip
+    # (an instance sitting on a switching surface to within rounding) is allowed for < 1 %
+    assert modes_equal.mean() > 0.99
+    err = np.abs(q_roll.cpu().numpy() - q_orc)[:, modes_equal]
+    assert err.max() < 1e-9, err.max()
+
+
+def test_rollout_with_virtual_variable():
+    torch = _torch()
+    t, p, dp = cs.MX.sym("t"), cs.MX.sym("p"), cs.MX.sym("dp")
+    x, dx = cs.MX.sym("x"), cs.MX.sym("dx")
+    up = cc.EqualityConstraint("move_up_path_cnstr", 300 - x, gain=1.0, priority=1)
+    lim = cc.SetConstraint("cart_limit_cnstr", p, gain=1.0, set_min=0.0, set_max=1.0, priority=1)
+    dist = cc.EqualityConstraint("min_dist_cnstr", 0.4 * cs.sin(0.3 * x) - p, gain=1.0, priority=3)
+    spec = cc.SkillSpecification("path", t, p, robot_vel_var=dp, virtual_var=x, virtual_vel_var=dx,
+                                 constraints=[up, dist, lim])
+    ctrl = cc.PseudoInverseController(spec)
+    ctrl.setup_solver()
+    N, K, dt = 64, 100, 0.02
+    p0 = torch.full((1, N), 0.0001, dtype=torch.float64, device="cuda")
+    x0 = torch.linspace(0, 5, N, dtype=torch.float64, device="cuda").reshape(1, N).contiguous()
+    pl, xl = p0.clone(), x0.clone()
+    out = ctrl.rollout_batch(0.0, p0, K, dt, virtual_var=x0, max_speed=0.275, max_virtual_speed=0.5)
+    for k in range(K):
+        v, xd, _ = ctrl.solve_batch(dt * k, pl, xl)
+        pl = pl + torch.clamp(v, -0.275, 0.275) * dt
+        xl = xl + torch.clamp(xd, -0.5, 0.5) * dt
+    assert torch.equal(p0, pl) and torch.equal(x0, xl)
+    assert bool((x0 > xl.new_tensor(0.9)).all())          # the path variable advanced at its speed limit
+    assert out["virtual_vel"].shape == (1, N)

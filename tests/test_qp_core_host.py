@@ -1,0 +1,134 @@
+"""The QP kernel's algorithm (csrc/clik_qp.cuh: qp_dual_active_set) compiled for the HOST with g++
+and a few shims, exercised against the oracle on problem classes that are awkward to reach through
+a robot skill: +-inf and +-1e10 bounds, equality rows, duplicated and linearly dependent rows, more
+rows than variables, infeasible sets.  This is a test harness for the device code's logic, not a
+product path (the product has no CPU fallback)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle_bridge import orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = r'''
+#include <cmath>
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+struct D3 { unsigned x = 1; };
+static D3 gridDim, blockDim, blockIdx, threadIdx;
+static inline double __ldcs(const double* p) { return *p; }
+static inline void __stcs(double* p, double v) { *p = v; }
+static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+using std::fma; using std::fmax; using std::fmin; using std::fabs; using std::sqrt;
+#include "%s"
+extern "C" int host_qp(int nx, int m, double* A, const double* lb, const double* ub, const double* h,
+                       double* x, unsigned* au, unsigned* al, int max_iter) {
+  return clik::qp_dual_active_set<16, 32>(nx, m, A, lb, ub, h, nullptr, x, au, al, max_iter);
+}
+'''
+
+
+@pytest.fixture(scope="module")
+def host_qp(tmp_path_factory):
+    d = tmp_path_factory.mktemp("qp_host")
+    src = d / "host_qp.cpp"
+    src.write_text(SHIM % os.path.join(ROOT, "casclik_b200", "csrc", "clik_qp.cuh"))
+    so = d / "host_qp.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", str(so), str(src)], check=True)
+    lib = ctypes.CDLL(str(so))
+
+    def solve(h, A, lb, ub, max_iter=400):
+        m, n = A.shape
+        Ac = np.ascontiguousarray(A, dtype=np.float64).copy()
+        x = np.zeros(n)
+        au, al = ctypes.c_uint(), ctypes.c_uint()
+        p = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        lbc, ubc, hc = (np.ascontiguousarray(v, dtype=np.float64) for v in (lb, ub, h))
+        st = lib.host_qp(n, m, Ac.ctypes.data_as(ctypes.c_void_p), lbc.ctypes.data_as(ctypes.c_void_p),
+                         ubc.ctypes.data_as(ctypes.c_void_p), hc.ctypes.data_as(ctypes.c_void_p),
+                         x.ctypes.data_as(ctypes.c_void_p), ctypes.byref(au), ctypes.byref(al), max_iter)
+        return x, st, au.value, al.value
+    return solve
+
+
+def _masks(lam):
+    up = sum(1 << r for r in range(len(lam)) if lam[r] > 0)
+    lo = sum(1 << r for r in range(len(lam)) if lam[r] < 0)
+    return up, lo
+
+
+def _check(host_qp, h, A, lb, ub, flags=True):
+    x, st, au, al = host_qp(h, A, lb, ub)
+    xo, lamo, sto = orc.solve_qp_single(h, A, lb, ub)
+    assert st == 0 and sto == 0
+    kk = orc.kkt_residuals(h, A, lb, ub, x)
+    assert kk["primal"] < 1e-9 and kk["stationarity"] < 1e-9 and kk["sign"] < 1e-9, kk
+    assert np.abs(x - xo).max() < 1e-9 * (1 + np.abs(xo).max())
+    if flags:
+        assert (au, al) == _masks(lamo)
+
+
+def test_random_problems_with_infinite_huge_and_equality_bounds(host_qp):
+    rng = np.random.default_rng(5)
+    for trial in range(300):
+        n, m = int(rng.integers(1, 10)), int(rng.integers(1, 16))
+        h = rng.uniform(0.001, 2.0, n)
+        A = rng.normal(size=(m, n))
+        r = A @ rng.normal(size=n)
+        lb, ub = r - rng.uniform(0, 1, m), r + rng.uniform(0, 1, m)
+        for i in range(m):
+            c = rng.random()
+            if c < 0.1:
+                lb[i] = -np.inf
+            elif c < 0.2:
+                ub[i] = np.inf
+            elif c < 0.3:
+                lb[i], ub[i] = -1e10, 1e10
+            elif c < 0.4:
+                lb[i] = ub[i] = r[i]
+        _check(host_qp, h, A, lb, ub)
+
+
+def test_duplicate_and_dependent_rows(host_qp):
+    rng = np.random.default_rng(7)
+    for trial in range(100):
+        n = int(rng.integers(2, 8))
+        A0 = rng.normal(size=(4, n))
+        A = np.vstack([A0, A0[0], 2.0 * A0[1], A0[2] + A0[3]])      # rows 4..6 depend on rows 0..3
+        x_in = rng.normal(size=n)
+        r = A @ x_in
+        lb, ub = r - rng.uniform(0.01, 1, 7), r + rng.uniform(0.01, 1, 7)
+        h = rng.uniform(0.01, 1.0, n)
+        x, st, au, al = host_qp(h, A, lb, ub)
+        assert st == 0
+        kk = orc.kkt_residuals(h, A, lb, ub, x)
+        assert kk["primal"] < 1e-9
+        xo, _, sto = orc.solve_qp_single(h, A, lb, ub)
+        assert sto == 0 and np.abs(x - xo).max() < 1e-8 * (1 + np.abs(xo).max())
+
+
+def test_more_active_rows_than_variables_and_infeasible(host_qp):
+    # box in 2-D cut by many half-planes: feasible, vertex solutions with degenerate ties
+    A = np.array([[1., 0.], [0., 1.], [1., 1.], [1., -1.], [2., 1.], [1., 2.]])
+    lb = np.array([1., 1., 2., -5., 3., 3.])
+    ub = np.full(6, 50.0)
+    x, st, _, _ = host_qp(np.array([1.0, 1.0]), A, lb, ub)
+    assert st == 0 and np.allclose(x, [1.0, 1.0], atol=1e-12)
+    # contradictory rows -> infeasible status, never a wrong "solved"
+    x, st, _, _ = host_qp(np.ones(2), np.array([[1., 0.], [1., 0.]]), np.array([1., -3.]), np.array([2., -2.]))
+    assert st == 2
+    # unconstrained optimum already feasible: zero iterations, nothing active
+    x, st, au, al = host_qp(np.ones(3), np.eye(3), -np.ones(3), np.ones(3))
+    assert st == 0 and np.all(x == 0.0) and au == 0 and al == 0
+    # iteration cap is reported
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(12, 6))
+    r = A @ rng.normal(size=6)
+    x, st, _, _ = host_qp(np.ones(6), A, r + 0.5, r + 1.0)
+    assert st == 0
+    _, st1, _, _ = host_qp(np.ones(6), A, r + 0.5, r + 1.0, 1)
+    assert st1 == 1
