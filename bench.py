@@ -264,7 +264,13 @@ def main():
                 if meta["n_virtual"] else None,
                 torch.empty((B,), dtype=torch.int32).pin_memory().numpy())
         d2h = B * (8 * (meta["n_robot"] + meta["n_virtual"]) + 4)
-    h2d = sum(v.nbytes for v in host.values() if v is not None)
+    # the host ABI copies only the input rows the compiled kernel reads (read masks in the cubin)
+    mk = meta["qp_read_masks" if is_qp else "pinv_read_masks"]
+    rows_in = (mk[0] if host["t"].size > 1 else 0)
+    for mask, key in ((mk[1], "q"), (mk[2], "x"), (mk[3], "y")):
+        if host[key] is not None:
+            rows_in += bin(mask & ((1 << host[key].shape[0]) - 1)).count("1")
+    h2d = 8 * B * rows_in + (8 if (mk[0] and host["t"].size == 1) else 0)
 
     def e2e_step():
         ctrl.solve_batch(host["t"], host["q"], host["x"], host["y"], out=hout)

@@ -206,6 +206,14 @@ class Emitter(object):
                 stack.extend(re.findall(r"v\d+", rhs))
         return seen
 
+    def read_masks(self, syms):
+        """(t, q, x, y) bit masks of the input rows the emitted program reads."""
+        ids = {n.id for n in dag.symbols_of(getattr(self, "roots", []))}
+        def mask(nodes):
+            return sum(1 << j for j, n in enumerate(nodes) if n.id in ids and j < 32) | \
+                (0xffffffff ^ ((1 << min(len(nodes), 32)) - 1) if len(nodes) > 32 else 0)
+        return (1 if syms.t[0].id in ids else 0, mask(syms.q), mask(syms.x), mask(syms.y))
+
     def inputs_read(self):
         """Number of distinct input scalars (t, q_i, x_i, y_i) the emitted program reads: loads of
         unused inputs are dead code in the kernel, so only these count as algorithmic traffic."""
@@ -358,6 +366,15 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out.append(_switch("row0", [b["row0"] for b in pinv.blocks]))
         out.append(_switch("rows", [b["rows"] for b in pinv.blocks]))
         out.append(_switch("set_index", [max(b["set_index"], 0) for b in pinv.blocks]))
+        eq_slots, nxt = [], 0
+        for b in pinv.blocks:
+            if b["kind"] in (KIND_EQ, KIND_VELEQ):
+                eq_slots.append(nxt)
+                nxt += 1
+            else:
+                eq_slots.append(0)
+        out.append("  static constexpr int NEQC = %d;   // Eq / VelEq constraints" % nxt)
+        out.append(_switch("eq_index", eq_slots))
         rowmask = []
         for b in pinv.blocks:
             for r in range(b["rows"]):
@@ -374,6 +391,17 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         pre_struct.append("__device__ const unsigned short clik_mode_tab[%d] = {%s};" % (
             len(masks), ", ".join(str(v) for v in masks)))
         out.append("  __device__ static __forceinline__ unsigned mode_mask(int mi) { return clik_mode_tab[mi]; }")
+        # modes compiled on the static register path: all of them when there are at most 8,
+        # otherwise those with at most two active sets if that is at most 64 modes (iiwa: 29 of
+        # 128, which covers 99.6 % of the random instances of configs[2]), else mode 0 + singles
+        ns_ = pinv.n_sets
+        upto2 = 1 + ns_ + ns_ * (ns_ - 1) // 2
+        default_static = len(masks) if len(masks) <= 8 else (upto2 if upto2 <= 64 else 1 + ns_)
+        n_static = int(os.environ.get("CLIK_NSTATIC", "0")) or default_static
+        n_static = max(1, min(n_static, len(masks)))
+        meta["pinv_static_modes"] = n_static
+        out.append("  static constexpr int NSTATIC = %d;   // leading modes instantiated on the static path" % n_static)
+        out.append(_switch("static_mask", masks[:n_static], ret="unsigned"))
         em = Emitter(pinv.syms.names, const_table, sincos_name)
         body = []
         for b in pinv.blocks:
@@ -421,6 +449,7 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
             else:
                 out.append("    %s = b[%d][tid];" % (lv, k))
         out.append("  }")
+        meta["pinv_read_masks"] = em.read_masks(pinv.syms)
         meta["pinv_staged_rows"] = len(staged)
         meta["pinv_t_read"] = t_staged
         cnt = em.counts()
@@ -447,6 +476,7 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out += ["    " + ln for ln in em.finish()]
         out.append("  }")
         meta["qp_eval"] = em.counts()
+        meta["qp_read_masks"] = em.read_masks(qp.syms)
         meta["qp_inputs_read"] = em.inputs_read()
         meta["qp_bytes_per_step"] = 8 * em.inputs_read() + 8 * qp.nx + 4 + 8
 
@@ -472,12 +502,14 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out.append("  clik::pinv_rollout<Skill>(N, steps, dt, t0, t_stride, q, x, y, vmax_q, vmax_x, qdot_last,")
         out.append("                            xdot_last, mode_last, n_failed);")
         out.append("}")
-        out.append('extern "C" __global__ void %s clik_pinv_tma_kernel(' % bounds)
-        out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
-        out.append("    const double* y, double* qdot, double* xdot, int* mode) {")
-        out.append("  clik::pinv_step_tma<Skill, %d, %d>(N, t, t_stride, q, x, y, qdot, xdot, mode);"
-                   % (block_threads, int(os.environ.get("CLIK_STAGES", "2"))))
-        out.append("}")
+        if os.environ.get("CLIK_TMA", "0") == "1":
+            # opt-in TMA-staged persistent variant (measured slower than the plain kernel)
+            out.append('extern "C" __global__ void %s clik_pinv_tma_kernel(' % bounds)
+            out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
+            out.append("    const double* y, double* qdot, double* xdot, int* mode) {")
+            out.append("  clik::pinv_step_tma<Skill, %d, %d>(N, t, t_stride, q, x, y, qdot, xdot, mode);"
+                       % (block_threads, int(os.environ.get("CLIK_STAGES", "2"))))
+            out.append("}")
     if qp is not None:
         out.append('extern "C" __global__ void __launch_bounds__(%d) clik_qp_kernel(' % block_threads)
         out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
@@ -488,6 +520,10 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
     out.append('extern "C" __global__ void clik_sizes_kernel(int* o) {')
     out.append("  o[0] = %d; o[1] = %d; o[2] = %d; o[3] = %d; o[4] = %d; o[5] = %d; o[6] = %d; o[7] = 0;"
                % (nq, nxv, ny, meta["n_modes"], meta["qp_n"], meta["qp_m"], meta.get("pinv_unroll", 1)))
+    full = (1, 0xffffffff, 0xffffffff, 0xffffffff)
+    pm, qm = meta.get("pinv_read_masks", full), meta.get("qp_read_masks", full)
+    out.append("  // input rows the kernels read (t, q, x, y bit masks): pinv then QP")
+    out.append("  " + " ".join("o[%d] = (int)0x%xu;" % (8 + k, v) for k, v in enumerate(tuple(pm) + tuple(qm))))
     out.append("}")
     return "\n".join(out) + "\n", meta
 

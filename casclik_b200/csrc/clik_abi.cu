@@ -52,10 +52,16 @@ struct KernelInfo {
 };
 
 // device scratch for the host-buffer pipeline (two slots, sized on demand)
+constexpr int NSLOTS = 4;
 struct Scratch {
-  void* dev[2] = {nullptr, nullptr};
-  size_t bytes[2] = {0, 0};
-  cudaStream_t stream[2] = {nullptr, nullptr};
+  void* dev[NSLOTS] = {nullptr};
+  size_t bytes[NSLOTS] = {0};
+  cudaStream_t stream[NSLOTS] = {nullptr};
+};
+
+// input rows read by the compiled kernels (bit j = row j), exported by the cubin's size probe
+struct ReadMask {
+  unsigned t = 1u, q = 0xffffffffu, x = 0xffffffffu, y = 0xffffffffu;
 };
 
 }  // namespace
@@ -64,6 +70,7 @@ struct clik_skill {
   clik_skill_desc desc;
   cudaLibrary_t lib = nullptr;
   KernelInfo pinv, pinv_tma, pinv_rollout, qp;
+  ReadMask pinv_reads, qp_reads;
   bool use_tma = false;  // opt-in (CLIK_TMA=1): measured slower than the plain kernel, see DESIGN.md
   int sm_count = 0;
   std::mutex mu;  // guards scratch
@@ -177,6 +184,7 @@ struct Field {
   int elem;          // bytes per element
   int stride;        // 1 = per instance, 0 = broadcast scalar row (only for t)
   size_t dev_off;    // byte offset inside the slot buffer
+  unsigned rowmask = 0xffffffffu;  // input rows the kernel reads (unread rows are not copied)
 };
 
 clik_status ensure_scratch(clik_skill* s, int slot, size_t bytes) {
@@ -192,36 +200,65 @@ clik_status ensure_scratch(clik_skill* s, int slot, size_t bytes) {
   return CLIK_OK;
 }
 
-constexpr int64_t HOST_CHUNK = 1 << 19;
+// Chunk size of the host pipeline: small enough that H2D of chunk k+1, the kernel of chunk k and
+// D2H of chunk k-1 overlap (both copy engines busy), large enough to amortise launch overheads.
+int64_t host_chunk() {
+  static int64_t v = [] {
+    const char* e = getenv("CLIK_HOST_CHUNK");
+    int64_t c = e ? atoll(e) : (1 << 17);
+    return c < 1024 ? (int64_t)1024 : c;
+  }();
+  return v;
+}
+
+// copy the rows selected by `mask` as maximal runs of consecutive rows
+template <class Copy>
+clik_status for_row_runs(int rows, unsigned mask, Copy copy) {
+  int r = 0;
+  while (r < rows) {
+    if (r < 32 && !((mask >> r) & 1u)) { ++r; continue; }
+    int e = r + 1;
+    while (e < rows && (e >= 32 || ((mask >> e) & 1u))) ++e;
+    clik_status st = copy(r, e - r);
+    if (st != CLIK_OK) return st;
+    r = e;
+  }
+  return CLIK_OK;
+}
 
 template <class Launch>
 clik_status run_host_pipeline(clik_skill* s, int64_t N, std::vector<Field>& f, Launch launch) {
   std::lock_guard<std::mutex> lock(s->mu);
   CK(cudaSetDevice(s->desc.device));
-  const int64_t chunk = std::min<int64_t>(N, HOST_CHUNK);
+  const int64_t chunk = std::min<int64_t>(N, host_chunk());
   size_t bytes = 0;
   for (auto& fl : f) {
     fl.dev_off = bytes;
     bytes += (((size_t)fl.rows * chunk * fl.elem) + 255) & ~(size_t)255;
   }
-  for (int slot = 0; slot < 2; ++slot) {
+  const int nslots = (int)std::min<int64_t>(NSLOTS, (N + chunk - 1) / chunk);
+  for (int slot = 0; slot < nslots; ++slot) {
     clik_status st = ensure_scratch(s, slot, bytes);
     if (st != CLIK_OK) return st;
   }
   int slot = 0;
-  for (int64_t i0 = 0; i0 < N; i0 += chunk, slot ^= 1) {
+  for (int64_t i0 = 0; i0 < N; i0 += chunk, slot = (slot + 1) % nslots) {
     const int64_t c = std::min<int64_t>(chunk, N - i0);
     cudaStream_t st = s->scratch.stream[slot];
     char* base = (char*)s->scratch.dev[slot];
     for (auto& fl : f) {
       if (!fl.src) continue;
       if (fl.stride == 0) {
-        CK(cudaMemcpyAsync(base + fl.dev_off, fl.src, fl.elem, cudaMemcpyHostToDevice, st));
-      } else {
-        CK(cudaMemcpy2DAsync(base + fl.dev_off, (size_t)c * fl.elem,
-                             (const char*)fl.src + (size_t)i0 * fl.elem, (size_t)N * fl.elem,
-                             (size_t)c * fl.elem, fl.rows, cudaMemcpyHostToDevice, st));
+        if (fl.rowmask & 1u) CK(cudaMemcpyAsync(base + fl.dev_off, fl.src, fl.elem, cudaMemcpyHostToDevice, st));
+        continue;
       }
+      clik_status cs = for_row_runs(fl.rows, fl.rowmask, [&](int r0, int nr) -> clik_status {
+        CK(cudaMemcpy2DAsync(base + fl.dev_off + (size_t)r0 * c * fl.elem, (size_t)c * fl.elem,
+                             (const char*)fl.src + ((size_t)r0 * N + (size_t)i0) * fl.elem,
+                             (size_t)N * fl.elem, (size_t)c * fl.elem, nr, cudaMemcpyHostToDevice, st));
+        return CLIK_OK;
+      });
+      if (cs != CLIK_OK) return cs;
     }
     clik_status ls = launch(base, c, st);
     if (ls != CLIK_OK) return ls;
@@ -232,8 +269,7 @@ clik_status run_host_pipeline(clik_skill* s, int64_t N, std::vector<Field>& f, L
                            cudaMemcpyDeviceToHost, st));
     }
   }
-  CK(cudaStreamSynchronize(s->scratch.stream[0]));
-  CK(cudaStreamSynchronize(s->scratch.stream[1]));
+  for (int k = 0; k < nslots; ++k) CK(cudaStreamSynchronize(s->scratch.stream[k]));
   return CLIK_OK;
 }
 
@@ -292,7 +328,7 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
     cudaKernel_t probe;
     if (cudaLibraryGetKernel(&probe, s->lib, "clik_sizes_kernel") == cudaSuccess) {
       int* dsz = nullptr;
-      int hsz[8] = {0};
+      int hsz[16] = {0};
       if (cudaMalloc(&dsz, sizeof(hsz)) == cudaSuccess) {
         void* args[] = {&dsz};
         cudaError_t le = cudaLaunchKernel((const void*)probe, dim3(1), dim3(1), args, 0, nullptr);
@@ -300,7 +336,10 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
         cudaFree(dsz);
         if (le != cudaSuccess) {
           st = fail(CLIK_ERR_CUDA, "size probe failed: %s", cudaGetErrorString(le));
-        } else if ((s->pinv.unroll = hsz[6] > 0 ? hsz[6] : 1), hsz[0] != desc->n_robot || hsz[1] != desc->n_virtual || hsz[2] != desc->n_input ||
+        } else if ((s->pinv.unroll = hsz[6] > 0 ? hsz[6] : 1),
+                   (s->pinv_reads = ReadMask{(unsigned)hsz[8], (unsigned)hsz[9], (unsigned)hsz[10], (unsigned)hsz[11]}),
+                   (s->qp_reads = ReadMask{(unsigned)hsz[12], (unsigned)hsz[13], (unsigned)hsz[14], (unsigned)hsz[15]}),
+                   hsz[0] != desc->n_robot || hsz[1] != desc->n_virtual || hsz[2] != desc->n_input ||
                    hsz[3] != desc->n_modes || hsz[4] != desc->qp_n || hsz[5] != desc->qp_m) {
           st = fail(CLIK_ERR_IMAGE,
                     "descriptor does not match cubin: image (n_robot %d, n_virtual %d, n_input %d, "
@@ -324,7 +363,7 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
 void clik_skill_free(clik_skill* s) {
   if (!s) return;
   cudaSetDevice(s->desc.device);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < NSLOTS; ++i) {
     if (s->scratch.dev[i]) cudaFree(s->scratch.dev[i]);
     if (s->scratch.stream[i]) cudaStreamDestroy(s->scratch.stream[i]);
   }
@@ -439,6 +478,10 @@ clik_status clik_pinv_step_host(const clik_skill* cs, int64_t N, const double* t
   f.push_back({q, nullptr, d.n_robot, 8, 1, 0});
   f.push_back({d.n_virtual ? x : nullptr, nullptr, d.n_virtual, 8, 1, 0});
   f.push_back({d.n_input ? y : nullptr, nullptr, d.n_input, 8, 1, 0});
+  f[0].rowmask = s->pinv_reads.t;
+  f[1].rowmask = s->pinv_reads.q;
+  f[2].rowmask = s->pinv_reads.x;
+  f[3].rowmask = s->pinv_reads.y;
   f.push_back({nullptr, qdot, d.n_robot, 8, 1, 0});
   f.push_back({nullptr, d.n_virtual ? xdot : nullptr, d.n_virtual, 8, 1, 0});
   f.push_back({nullptr, mode, 1, 4, 1, 0});
@@ -466,6 +509,10 @@ clik_status clik_qp_step_host(const clik_skill* cs, int64_t N, const double* t, 
   f.push_back({q, nullptr, d.n_robot, 8, 1, 0});
   f.push_back({d.n_virtual ? x : nullptr, nullptr, d.n_virtual, 8, 1, 0});
   f.push_back({d.n_input ? y : nullptr, nullptr, d.n_input, 8, 1, 0});
+  f[0].rowmask = s->qp_reads.t;
+  f[1].rowmask = s->qp_reads.q;
+  f[2].rowmask = s->qp_reads.x;
+  f[3].rowmask = s->qp_reads.y;
   f.push_back({x0, nullptr, d.qp_n, 8, 1, 0});
   f.push_back({nullptr, sol, d.qp_n, 8, 1, 0});
   f.push_back({nullptr, status, 1, 4, 1, 0});

@@ -280,11 +280,35 @@ __device__ __forceinline__ void first_equality_twice(const double (&J)[Max<S::M 
   }
 }
 
+// P(J_c) des_c of every Eq / VelEq constraint.  It does not depend on the mode (only the null-space
+// projector does), so skills with SetConstraints compute it once per instance and every mode that
+// is tried reuses it.
+template <class S> struct TaskVel {
+  double w[Max<S::NEQC, 1>::v][S::NS];
+};
+
+template <class S, int C = 0>
+__device__ __forceinline__ void compute_task_vel(const PinvData<S>& d, TaskVel<S>& tw) {
+  if constexpr (C < S::NC) {
+    constexpr int kind = S::kind(C);
+    if constexpr (kind == KIND_EQ || kind == KIND_VELEQ) {
+      constexpr int r0 = S::row0(C);
+      constexpr int m = S::rows(C);
+      using RC = typename Range<r0, m>::type;
+      double b[Max<m, 1>::v];
+#pragma unroll
+      for (int a = 0; a < m; ++a) b[a] = d.des[r0 + a];
+      pinv_times<S, RC>(d.J, b, tw.w[S::eq_index(C)]);
+    }
+    compute_task_vel<S, C + 1>(d, tw);
+  }
+}
+
 // ---- one mode, mode mask known at compile time -----------------------------------------------------
 // Walks the priority-sorted constraint table exactly like the reference's loop
 // (pseudo_inverse.py:274-443), with the active-row list carried as a type.
-template <class S, unsigned MASK, int C, class Stack> struct StaticMode {
-  __device__ __forceinline__ static void run(const PinvData<S>& d, double (&v)[S::NS]) {
+template <class S, unsigned MASK, int C, class Stack, bool PRE> struct StaticMode {
+  __device__ __forceinline__ static void run(const PinvData<S>& d, const TaskVel<S>& tw, double (&v)[S::NS]) {
     if constexpr (C < S::NC) {
       constexpr int kind = S::kind(C);
       constexpr int r0 = S::row0(C);
@@ -299,40 +323,55 @@ template <class S, unsigned MASK, int C, class Stack> struct StaticMode {
           using S1 = typename Concat<Stack, RC>::type;
           if constexpr (kind == KIND_EQ) {
             // :322-326 and, because the reference's next chain starts with a new `if`, :382-396
-            if constexpr (S::FUSE_FIRST_EQ) {
+            if constexpr (S::FUSE_FIRST_EQ && !PRE) {
               first_equality_twice<S, RC>(d.J, b, w);
 #pragma unroll
               for (int j = 0; j < S::NS; ++j) v[j] += w[j];
             } else {
-              pinv_times<S, RC>(d.J, b, w);
+              if constexpr (PRE) {
+#pragma unroll
+                for (int j = 0; j < S::NS; ++j) w[j] = tw.w[S::eq_index(C)][j];
+              } else {
+                pinv_times<S, RC>(d.J, b, w);
+              }
 #pragma unroll
               for (int j = 0; j < S::NS; ++j) v[j] += w[j];
               nullspace_apply<S, S1>(d.J, w);
 #pragma unroll
               for (int j = 0; j < S::NS; ++j) v[j] += w[j];
             }
-            StaticMode<S, MASK, C + 1, typename Concat<S1, RC>::type>::run(d, v);
+            StaticMode<S, MASK, C + 1, typename Concat<S1, RC>::type, PRE>::run(d, tw, v);
           } else {
-            pinv_times<S, RC>(d.J, b, w);                                // :331-335
+            if constexpr (PRE) {
+#pragma unroll
+              for (int j = 0; j < S::NS; ++j) w[j] = tw.w[S::eq_index(C)][j];
+            } else {
+              pinv_times<S, RC>(d.J, b, w);                              // :331-335
+            }
 #pragma unroll
             for (int j = 0; j < S::NS; ++j) v[j] += w[j];
-            StaticMode<S, MASK, C + 1, S1>::run(d, v);
+            StaticMode<S, MASK, C + 1, S1, PRE>::run(d, tw, v);
           }
         } else {
-          pinv_times<S, RC>(d.J, b, w);
+          if constexpr (PRE) {
+#pragma unroll
+            for (int j = 0; j < S::NS; ++j) w[j] = tw.w[S::eq_index(C)][j];
+          } else {
+            pinv_times<S, RC>(d.J, b, w);
+          }
           nullspace_apply<S, Stack>(d.J, w);                              // :387-394 / :434-441
 #pragma unroll
           for (int j = 0; j < S::NS; ++j) v[j] += w[j];
-          StaticMode<S, MASK, C + 1, typename Concat<Stack, RC>::type>::run(d, v);
+          StaticMode<S, MASK, C + 1, typename Concat<Stack, RC>::type, PRE>::run(d, tw, v);
         }
       } else if constexpr (kind == KIND_SET) {
         if constexpr ((MASK >> S::set_index(C)) & 1u) {                   // :399-405
-          StaticMode<S, MASK, C + 1, typename Concat<Stack, RC>::type>::run(d, v);
+          StaticMode<S, MASK, C + 1, typename Concat<Stack, RC>::type, PRE>::run(d, tw, v);
         } else {
-          StaticMode<S, MASK, C + 1, Stack>::run(d, v);
+          StaticMode<S, MASK, C + 1, Stack, PRE>::run(d, tw, v);
         }
       } else {
-        StaticMode<S, MASK, C + 1, Stack>::run(d, v);                     // VelocitySet: ignored
+        StaticMode<S, MASK, C + 1, Stack, PRE>::run(d, tw, v);            // VelocitySet: ignored
       }
     }
   }
@@ -343,11 +382,11 @@ __device__ __forceinline__ bool in_tangent_cone(double e, double de, double smin
   return (smin - e < 1e-12) ? ((e - smax < 1e-12) ? true : (de < 0.0)) : (de > 0.0);
 }
 
-template <class S, unsigned MASK>
-__device__ __forceinline__ bool static_mode(const PinvData<S>& d, double (&v)[S::NS]) {
+template <class S, unsigned MASK, bool PRE>
+__device__ __forceinline__ bool static_mode(const PinvData<S>& d, const TaskVel<S>& tw, double (&v)[S::NS]) {
 #pragma unroll
   for (int j = 0; j < S::NS; ++j) v[j] = 0.0;
-  StaticMode<S, MASK, 0, Rows<>>::run(d, v);
+  StaticMode<S, MASK, 0, Rows<>, PRE>::run(d, tw, v);
   bool ok = true;
 #pragma unroll
   for (int c = 0; c < S::NC; ++c) {
@@ -436,7 +475,7 @@ __device__ void dyn_pinv_times(const double* J, const int* rows, int K, const do
 }
 
 template <class S>
-__device__ __noinline__ bool dynamic_mode(const PinvData<S>* d, unsigned mask, double* v) {
+__device__ __noinline__ bool dynamic_mode(const PinvData<S>* d, const TaskVel<S>* tw, unsigned mask, double* v) {
   constexpr int NS = S::NS;
   constexpr int MAXK = S::M + S::MAXROWS;   // every row once + the doubled first equality
   int stack[MAXK];
@@ -446,9 +485,7 @@ __device__ __noinline__ bool dynamic_mode(const PinvData<S>* d, unsigned mask, d
   for (int c = 0; c < S::NC; ++c) {
     const int kind = S::kind(c), r0 = S::row0(c), m = S::rows(c);
     if (kind == KIND_EQ || kind == KIND_VELEQ) {
-      int own[S::MAXROWS];
-      for (int a = 0; a < m; ++a) own[a] = r0 + a;
-      dyn_pinv_times<S>(d->J, own, m, &d->des[r0], w);
+      for (int j = 0; j < NS; ++j) w[j] = tw->w[S::eq_index(c)][j];     // mode-independent, precomputed
       const bool first = (k == 0);
       if (first) {
         for (int j = 0; j < NS; ++j) v[j] += w[j];
@@ -483,30 +520,67 @@ __device__ __noinline__ bool dynamic_mode(const PinvData<S>* d, unsigned mask, d
 // ---- the step --------------------------------------------------------------------------------------
 // One instance, inputs already in registers: evaluate the skill, try mode 0 on the static path,
 // fall back to the run-time mode search, and return the accepted mode index (-1: none).
+// Run-time mode index -> statically instantiated mode (the first S::NSTATIC entries of the
+// activation map: mode 0 and the single-set modes, or every mode when there are at most 8).
+template <class S, int MI> struct StaticDispatch {
+  __device__ __forceinline__ static bool run(int mi, const PinvData<S>& d, const TaskVel<S>& tw,
+                                             double (&v)[S::NS]) {
+    if (mi == MI) return static_mode<S, S::static_mask(MI), (S::NSTATIC < S::NMODES)>(d, tw, v);
+    if constexpr (MI + 1 < S::NSTATIC) {
+      return StaticDispatch<S, MI + 1>::run(mi, d, tw, v);
+    } else {
+      return false;
+    }
+  }
+};
+
+// One instance, inputs already in registers: evaluate the skill once, then walk the activation map
+// in the reference's order (pseudo_inverse.py:530-550) until a mode passes its in-tangent-cone
+// tests.  Mode 0 and the other frequent modes run on the static register path; the rest use the
+// run-time path on a local-memory copy of the constraint data.  Returns the accepted mode index
+// (-1: none admissible, v = 0, pseudo_inverse.py:551-555).
 template <class S>
 __device__ __forceinline__ int solve_instance(const double tv, const double (&qv)[Max<S::NQ, 1>::v],
                                               const double (&xv)[Max<S::NX, 1>::v],
                                               const double (&yv)[Max<S::NY, 1>::v], double (&v)[S::NS]) {
   PinvData<S> d;
   S::eval(tv, qv, xv, yv, d);
-  int accepted = 0;
-  bool ok = static_mode<S, 0u>(d, v);
+  TaskVel<S> tw;
   if constexpr (S::NSETS > 0) {
-    if (!ok) {
-      accepted = -1;
-      PinvData<S> copy = d;     // the slow path indexes dynamically: keep `d` itself in registers
-      double vd[S::NS];
-      for (int mi = 1; mi < S::NMODES; ++mi) {
-        if (dynamic_mode<S>(&copy, S::mode_mask(mi), vd)) {
-          accepted = mi;
-          break;
+    // precompute the mode-independent task velocities only when many modes may be tried
+    constexpr bool PRE = S::NSTATIC < S::NMODES;
+    if constexpr (PRE) compute_task_vel<S>(d, tw);
+    if (static_mode<S, 0u, PRE>(d, tw, v)) return 0;
+    int accepted = -1;
+    for (int mi = 1; mi < S::NSTATIC; ++mi) {
+      if (StaticDispatch<S, 1 < S::NSTATIC ? 1 : 0>::run(mi, d, tw, v)) {
+        accepted = mi;
+        break;
+      }
+    }
+    if constexpr (S::NSTATIC < S::NMODES) {
+      if (accepted < 0) {
+        // the run-time path indexes dynamically: work on copies, keep `d` / `tw` in registers
+        PinvData<S> copy = d;
+        TaskVel<S> twc = tw;
+        for (int mi = S::NSTATIC; mi < S::NMODES; ++mi) {
+          if (dynamic_mode<S>(&copy, &twc, S::mode_mask(mi), v)) {
+            accepted = mi;
+            break;
+          }
         }
       }
-#pragma unroll
-      for (int j = 0; j < S::NS; ++j) v[j] = (accepted < 0) ? 0.0 : vd[j];
     }
+    if (accepted < 0) {
+#pragma unroll
+      for (int j = 0; j < S::NS; ++j) v[j] = 0.0;
+    }
+    return accepted;
+  } else {
+    // no SetConstraints: a single mode with no test to fail
+    static_mode<S, 0u, false>(d, tw, v);
+    return 0;
   }
-  return accepted;
 }
 
 template <class S>

@@ -128,7 +128,10 @@ def test_more_active_rows_than_variables_and_infeasible(host_qp):
     rng = np.random.default_rng(0)
     A = rng.normal(size=(12, 6))
     r = A @ rng.normal(size=6)
-    x, st, _, _ = host_qp(np.ones(6), A, r + 0.5, r + 1.0)
-    assert st == 0
-    _, st1, _, _ = host_qp(np.ones(6), A, r + 0.5, r + 1.0, 1)
+    x, st, _, _ = host_qp(np.ones(6), A, r - 0.1, r + 0.1)          # feasible (x_in), far from 0
+    assert st == 0 and orc.kkt_residuals(np.ones(6), A, r - 0.1, r + 0.1, x)["primal"] < 1e-9
+    _, st1, _, _ = host_qp(np.ones(6), A, r - 0.1, r + 0.1, 1)
     assert st1 == 1
+    # 12 narrow bands in 6-D that exclude each other: both solvers must say infeasible
+    _, st2, _, _ = host_qp(np.ones(6), A, r + 0.5, r + 1.0)
+    assert st2 == orc.solve_qp_single(np.ones(6), A, r + 0.5, r + 1.0)[2] == 2
