@@ -306,16 +306,23 @@ def main():
             flops, bytes_step = None, meta["qp_bytes_per_step"]
         else:
             flops, bytes_step = meta["pinv_flops_mode0"], meta["pinv_bytes_per_step"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tr = json.load(f)
+            if tr.get("scenario") == scenario.name and tr.get("batch") == B:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]   # bytes per launch, from ncu
         ach_gbs = bytes_step * B / sec / 1e9
         roof_hbm = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                    "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
                     "algorithmic_bytes_per_step": bytes_step}
         roof = roof_hbm
         detail = {"hbm": roof_hbm}
         if flops:
             ach_tf = flops * B / sec / 1e12
             roof_f = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                      "frac": ach_tf / fp64_peak, "traffic": None,
+                      "frac": ach_tf / fp64_peak, "traffic": traffic,
                       "peak_source": "measured in this run (DFMA micro-benchmark, clik_measure_fp64_peak; "
                                      "MEASURED_PEAKS.json has no fp64 entry)",
                       "algorithmic_flops_per_step": flops,

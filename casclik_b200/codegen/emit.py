@@ -517,6 +517,13 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out.append("    int max_iter) {")
         out.append("  clik::qp_step<Skill>(N, t, t_stride, q, x, y, x0, sol, status, active, max_iter);")
         out.append("}")
+    if qp is not None:
+        out.append('extern "C" __global__ void __launch_bounds__(%d) clik_qp_rollout_kernel(' % block_threads)
+        out.append("    long long N, int steps, double dt, const double* t0, int t_stride, double* q, double* x,")
+        out.append("    const double* y, double vmax_q, double vmax_x, double* sol_last, int* n_failed, int max_iter) {")
+        out.append("  clik::qp_rollout<Skill>(N, steps, dt, t0, t_stride, q, x, y, vmax_q, vmax_x, sol_last, n_failed,")
+        out.append("                          max_iter);")
+        out.append("}")
     out.append('extern "C" __global__ void clik_sizes_kernel(int* o) {')
     out.append("  o[0] = %d; o[1] = %d; o[2] = %d; o[3] = %d; o[4] = %d; o[5] = %d; o[6] = %d; o[7] = 0;"
                % (nq, nxv, ny, meta["n_modes"], meta["qp_n"], meta["qp_m"], meta.get("pinv_unroll", 1)))

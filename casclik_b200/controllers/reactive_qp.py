@@ -239,6 +239,30 @@ class ReactiveQPController(BaseController):
                                                 b.ptr(active), mi))
         return sol, status, active
 
+    def rollout_batch(self, time_var0, robot_var, steps, dt, virtual_var=None, input_var=None,
+                      max_speed=None, max_virtual_speed=None, max_iter=None):
+        """Closed-loop simulation on the device (see PseudoInverseController.rollout_batch):
+        robot_var / virtual_var (torch CUDA, (n, N)) are UPDATED IN PLACE.  Returns a dict with the
+        last QP solution `sol` (nx, N) and `n_failed` (steps whose QP was not solved: zero velocity)."""
+        import ctypes
+        skill = self._skill()
+        spec = self.skill_spec
+        b = Batch(spec.n_robot_var, self._nxv, self._ny, time_var0, robot_var, virtual_var,
+                  input_var if self._ny else None)
+        if not b.on_device:
+            raise ValueError("rollout_batch needs CUDA tensors (state is updated in place on the device)")
+        if self._nxv and virtual_var is None:
+            raise ValueError("the skill has a virtual_var: pass its initial value")
+        sol, failed = b.empty(self._qn), b.empty(0, "i32")
+        inf = float("inf")
+        mi = int(max_iter if max_iter is not None else self.options.get("max_iter", 0) or 0)
+        runtime.check(runtime.load_library().clik_qp_rollout(
+            skill.handle, b.N, int(steps), ctypes.c_double(float(dt)), b.tp, b.t_stride, b.qp, b.xp, b.yp,
+            ctypes.c_double(inf if max_speed is None else float(max_speed)),
+            ctypes.c_double(inf if max_virtual_speed is None else float(max_virtual_speed)),
+            b.ptr(sol), b.ptr(failed), mi, b.stream()))
+        return {"sol": sol, "n_failed": failed}
+
     def solve(self, time_var, robot_var, virtual_var=None, input_var=None,
               warmstart_robot_vel_var=None, warmstart_virtual_vel_var=None,
               warmstart_slack_var=None):

@@ -69,7 +69,7 @@ struct ReadMask {
 struct clik_skill {
   clik_skill_desc desc;
   cudaLibrary_t lib = nullptr;
-  KernelInfo pinv, pinv_tma, pinv_rollout, qp;
+  KernelInfo pinv, pinv_tma, pinv_rollout, qp, qp_rollout;
   ReadMask pinv_reads, qp_reads;
   bool use_tma = false;  // opt-in (CLIK_TMA=1): measured slower than the plain kernel, see DESIGN.md
   int sm_count = 0;
@@ -323,6 +323,13 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
       cudaGetLastError();
   }
   if (st == CLIK_OK && desc->has_qp) st = setup_kernel(s, "clik_qp_kernel", &s->qp);
+  if (st == CLIK_OK && desc->has_qp) {
+    cudaKernel_t probe_qr;
+    if (cudaLibraryGetKernel(&probe_qr, s->lib, "clik_qp_rollout_kernel") == cudaSuccess)
+      st = setup_kernel(s, "clik_qp_rollout_kernel", &s->qp_rollout);
+    else
+      cudaGetLastError();
+  }
   // the image carries its own sizes: refuse a descriptor that disagrees
   if (st == CLIK_OK) {
     cudaKernel_t probe;
@@ -441,6 +448,25 @@ clik_status clik_qp_step(const clik_skill* s, int64_t N, const double* t, int32_
   void* args[] = {&n, &t, &ts, &q, &x, &y, &x0, &sol, &status, &active, &mi};
   CK(cudaLaunchKernel((const void*)s->qp.kernel, dim3(grid_for(s->qp, N)), dim3(s->qp.block), args,
                       0, (cudaStream_t)stream));
+  return CLIK_OK;
+}
+
+clik_status clik_qp_rollout(const clik_skill* s, int64_t N, int32_t steps, double dt, const double* t0,
+                            int32_t t_stride, double* q, double* x, const double* y,
+                            double max_robot_speed, double max_virtual_speed, double* sol_last,
+                            int32_t* n_failed, int32_t max_iter, void* stream) {
+  clik_status st = check_common(s, N, t0, q, x, y);
+  if (st != CLIK_OK || N == 0) return st;
+  if (!s->qp_rollout.kernel) return fail(CLIK_ERR_INVALID, "skill was built without the QP rollout kernel");
+  if (steps < 0) return fail(CLIK_ERR_INVALID, "steps < 0");
+  CK(cudaSetDevice(s->desc.device));
+  long long n = N;
+  int ts = t_stride ? 1 : 0, k = steps;
+  int mi = max_iter > 0 ? max_iter : 10 * (s->desc.qp_n + s->desc.qp_m);
+  void* args[] = {&n, &k, &dt, &t0, &ts, &q, &x, &y, &max_robot_speed, &max_virtual_speed,
+                  &sol_last, &n_failed, &mi};
+  CK(cudaLaunchKernel((const void*)s->qp_rollout.kernel, dim3(grid_for(s->qp_rollout, N)),
+                      dim3(s->qp_rollout.block), args, 0, (cudaStream_t)stream));
   return CLIK_OK;
 }
 

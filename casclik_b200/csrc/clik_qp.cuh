@@ -216,4 +216,52 @@ __device__ __forceinline__ void qp_step(long long N, const double* __restrict__ 
   }
 }
 
+// Closed-loop rollout with the QP controller: `steps` times  sol = solve(t0 + k*dt, q, x, y);
+// v = clip(sol[:n], +-max_speed); q += v_rob*dt; x += v_virt*dt  (the notebooks' simulation loop,
+// ur5_moe2016_example2.ipynb cell 12).  A step whose QP is not solved (status != 0; the reference
+// would raise there) applies zero velocity and is counted in n_failed.
+template <class S>
+__device__ __forceinline__ void qp_rollout(long long N, int steps, double dt, const double* __restrict__ t0,
+                                           int t_stride, double* __restrict__ q, double* __restrict__ x,
+                                           const double* __restrict__ y, double vmax_q, double vmax_x,
+                                           double* __restrict__ sol_last, int* __restrict__ n_failed,
+                                           int max_iter) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    double qv[S::NQ > 0 ? S::NQ : 1], xv[S::NX > 0 ? S::NX : 1], yv[S::NY > 0 ? S::NY : 1];
+    const double t0v = t0[(long long)t_stride * i];
+    for (int j = 0; j < S::NQ; ++j) qv[j] = q[(long long)j * N + i];
+    for (int j = 0; j < S::NX; ++j) xv[j] = x[(long long)j * N + i];
+    for (int j = 0; j < S::NY; ++j) yv[j] = y[(long long)j * N + i];
+    double xs[S::QN];
+    for (int j = 0; j < S::QN; ++j) xs[j] = 0.0;
+    int failed = 0;
+    for (int k = 0; k < steps; ++k) {
+      const double tv = __dadd_rn(t0v, __dmul_rn(dt, (double)k));
+      QpData<S> d;
+      S::eval_qp(tv, qv, xv, yv, d);
+      unsigned mu, ml;
+      const int st = qp_dual_active_set<S::QN, S::QM>(S::QN, S::QM, d.A, d.lb, d.ub, d.h, nullptr, xs,
+                                                      &mu, &ml, max_iter);
+      if (st != QP_OK) {
+        ++failed;
+        for (int j = 0; j < S::QN; ++j) xs[j] = 0.0;
+      }
+      for (int j = 0; j < S::NQ; ++j) {
+        xs[j] = fmax(fmin(xs[j], vmax_q), -vmax_q);
+        qv[j] = __dadd_rn(qv[j], __dmul_rn(xs[j], dt));
+      }
+      for (int j = 0; j < S::NX; ++j) {
+        xs[S::NQ + j] = fmax(fmin(xs[S::NQ + j], vmax_x), -vmax_x);
+        xv[j] = __dadd_rn(xv[j], __dmul_rn(xs[S::NQ + j], dt));
+      }
+    }
+    for (int j = 0; j < S::NQ; ++j) q[(long long)j * N + i] = qv[j];
+    for (int j = 0; j < S::NX; ++j) x[(long long)j * N + i] = xv[j];
+    if (sol_last != nullptr)
+      for (int j = 0; j < S::QN; ++j) sol_last[(long long)j * N + i] = xs[j];
+    if (n_failed != nullptr) n_failed[i] = failed;
+  }
+}
+
 }  // namespace clik

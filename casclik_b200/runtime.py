@@ -31,7 +31,7 @@ class SkillDesc(ctypes.Structure):
 #: every symbol include/clik.h declares (tests check that the library exports all of them)
 EXPORTS = (
     "clik_skill_load", "clik_skill_free", "clik_pinv_step", "clik_pinv_rollout", "clik_qp_step",
-    "clik_qp_dense",
+    "clik_qp_rollout", "clik_qp_dense",
     "clik_pinv_step_host", "clik_qp_step_host", "clik_skill_launch_info",
     "clik_measure_fp64_peak", "clik_flush_l2", "clik_device_count", "clik_abi_version",
     "clik_last_error",
@@ -74,6 +74,9 @@ def load_library():
     lib.clik_pinv_rollout.restype = i32
     lib.clik_pinv_rollout.argtypes = [vp, i64, i32, ctypes.c_double, vp, i32, vp, vp, vp,
                                       ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, vp]
+    lib.clik_qp_rollout.restype = i32
+    lib.clik_qp_rollout.argtypes = [vp, i64, i32, ctypes.c_double, vp, i32, vp, vp, vp,
+                                    ctypes.c_double, ctypes.c_double, vp, vp, i32, vp]
     lib.clik_qp_step.restype = i32
     lib.clik_qp_step.argtypes = [vp, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.clik_qp_step_host.restype = i32

@@ -108,6 +108,14 @@ clik_status clik_qp_step(const clik_skill* skill, int64_t N, const double* t, in
                          double* sol, int32_t* status, uint32_t* active, int32_t max_iter,
                          void* stream);
 
+/* The same simulation loop with the QP controller (see clik_pinv_rollout).  A step whose QP is not
+ * solved applies zero velocity and is counted in n_failed (the reference would raise there).
+ *   sol_last [qp_n * N] out, may be NULL: solution of the last step (robot part clipped) */
+clik_status clik_qp_rollout(const clik_skill* skill, int64_t N, int32_t steps, double dt,
+                            const double* t0, int32_t t_stride, double* q, double* x, const double* y,
+                            double max_robot_speed, double max_virtual_speed, double* sol_last,
+                            int32_t* n_failed, int32_t max_iter, void* stream);
+
 /* The conic call itself, `solver(h=H, a=A, lba=lb, uba=ub[, x0=])` (reactive_qp.py:493), for N
  * numeric problems of one shape: min 1/2 x' diag(h) x, lb <= A x <= ub.
  *   h [nx * N], A [(m * nx) * N] row-major per instance (entry (r, c) at A[(r*nx + c)*N + i]),

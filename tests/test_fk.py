@@ -80,3 +80,33 @@ def test_position_only_skill_prunes_to_a_small_program():
     flops = sum(h.get(k, 0) for k in ("add", "sub", "mul", "div", "sqrt"))
     assert flops <= 130 and h["sin"] == 5 and h["cos"] == 5
     assert all(n is dag.ZERO for n in J._a[:, 5])      # tool0 position does not depend on q6
+
+
+def test_pose_error_forms_of_the_notebooks():
+    from casclik_b200.fk import pose_errors as pe
+    d = fk.ur5()
+    q = cs.MX.sym("q", 6)
+    T, Q = d["T_fk"](q), d["dual_quaternion_fk"](q)
+    q_des = np.array([0.3, -1.2, 0.9, -0.4, 0.5, 0.1])
+    T_des = d["T_fk"](q_des).toarray()
+    Q_des = d["dual_quaternion_fk"](q_des).toarray()[:, 0]
+    forms = {"T_dist1": (pe.T_dist1(T, T_des), 1), "T_dist2": (pe.T_dist2(T, T_des), 4),
+             "T_dist3": (pe.T_dist3(T, T_des), 9), "Q_dist1": (pe.Q_dist1(Q, Q_des), 8),
+             "Q_dist2": (pe.Q_dist2(Q, Q_des), 8)}
+    f = cs.Function("f", [q], [e for e, _ in forms.values()])
+    at_target = f(q_des)
+    away = f(q_des + 0.2)
+    for (name, (e, rows)), z, a in zip(forms.items(), at_target, away):
+        assert e.shape == (rows, 1), name
+        assert np.abs(z.toarray()).max() < 1e-12, name          # every form vanishes at the target
+        assert np.abs(a.toarray()).max() > 1e-3, name
+    # T_dist2 against NumPy
+    Tn = d["T_fk"](q_des + 0.2).toarray()
+    ref = np.concatenate([Tn[:3, 3] - T_des[:3, 3],
+                          [np.linalg.norm(np.linalg.inv(T_des[:3, :3]) @ Tn[:3, :3] - np.eye(3))]])
+    assert np.abs(away[1].toarray()[:, 0] - ref).max() < 1e-13
+    # dual-quaternion algebra: A (x) B == dualH-(B) A, and unit norm of the FK quaternion
+    A, B = d["dual_quaternion_fk"](q_des + 0.2).toarray()[:, 0], Q_des
+    lhs = pe.dual_quaternion_product(A, B).toarray()[:, 0]
+    rhs = (pe.dual_hamilton_operator_minus(B).toarray() @ A)
+    assert np.abs(lhs - rhs).max() < 1e-14 and abs(np.linalg.norm(A[:4]) - 1.0) < 1e-14

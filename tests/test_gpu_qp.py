@@ -182,3 +182,25 @@ def test_conic_object_dense_random_problems():
         assert kk["primal"] < 1e-8 and kk["stationarity"] < 1e-8 and kk["sign"] < 1e-8
     res = solver(h=np.diag(h[0]), a=A[0], lba=lb[0], uba=ub[0])
     assert np.abs(res["x"].toarray()[:, 0] - x[0]).max() == 0.0
+
+
+def test_qp_rollout_on_device_matches_stepwise_loop():
+    torch = _torch()
+    sc = scenarios.get("ur5_moe2016_qp")
+    ctrl = sc.make_controller()
+    ctrl.setup_problem_functions()
+    ctrl.setup_solver()
+    N, K, dt, vmax = 128, 25, 0.008, np.pi / 5
+    inp = sc.sample(N, seed=4)
+    t0 = torch.from_numpy(inp["t"]).cuda()
+    q_roll = torch.from_numpy(inp["q"]).cuda()
+    q_loop = q_roll.clone()
+    out = ctrl.rollout_batch(t0, q_roll, K, dt, max_speed=vmax)
+    for k in range(K):
+        sol, status, _ = ctrl.solve_batch(t0 + dt * k, q_loop)
+        assert bool((status == 0).all())
+        v = torch.clamp(sol[:6], -vmax, vmax)
+        q_loop = q_loop + v * dt
+    torch.cuda.synchronize()
+    assert torch.equal(q_roll, q_loop)
+    assert torch.equal(out["sol"][:6], v) and int(out["n_failed"].sum()) == 0

@@ -23,6 +23,8 @@ static D3 gridDim, blockDim, blockIdx, threadIdx;
 static inline double __ldcs(const double* p) { return *p; }
 static inline void __stcs(double* p, double v) { *p = v; }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
 using std::fma; using std::fmax; using std::fmin; using std::fabs; using std::sqrt;
 #include "%s"
 extern "C" int host_qp(int nx, int m, double* A, const double* lb, const double* ub, const double* h,
