@@ -464,15 +464,40 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
     if qp is not None:
         meta["qp_n"], meta["qp_m"] = qp.nx, qp.m
         out.append("  static constexpr int QN = %d, QM = %d;" % (qp.nx, qp.m))
+        md, mu = len(qp.dense_rows), len(qp.unit_rows)
+        env = os.environ.get("CLIK_QP_STRUCT")
+        qstruct = (md <= 4 and qp.nx <= 12 and qp.m <= 32) if env is None else (env == "1")
+        meta["qp_structured"] = qstruct
+        meta["qp_dense_rows"], meta["qp_unit_rows"] = md, mu
+        out.append("  static constexpr bool QSTRUCT = %s;   // register-resident structured solver" %
+                   ("true" if qstruct else "false"))
         em = Emitter(qp.syms.names, const_table, sincos_name)
-        for r in range(qp.m):
+        if qstruct:
+            out.append("  static constexpr int QMD = %d, QMU = %d;   // dense rows, single-variable rows" % (md, mu))
+            out.append(_switch("dense_row", qp.dense_rows or [0]))
+            out.append(_switch("unit_row", [r for r, _, _ in qp.unit_rows] or [0]))
+            out.append(_switch("unit_col", [c for _, c, _ in qp.unit_rows] or [0]))
+            out.append(_switch("unit_coef", [literal(k) for _, _, k in qp.unit_rows] or ["1.0"], ret="double"))
+            for a, r in enumerate(qp.dense_rows):
+                for j in range(qp.nx):
+                    em.assign("d.Ad[%d]" % (a * qp.nx + j), qp.A[r][j])
+                em.assign("d.lbd[%d]" % a, qp.lb[r])
+                em.assign("d.ubd[%d]" % a, qp.ub[r])
+            for i, (r, _, _) in enumerate(qp.unit_rows):
+                em.assign("d.lbu[%d]" % i, qp.lb[r])
+                em.assign("d.ubu[%d]" % i, qp.ub[r])
             for j in range(qp.nx):
-                em.assign("d.A[%d]" % (r * qp.nx + j), qp.A[r][j])
-            em.assign("d.lb[%d]" % r, qp.lb[r])
-            em.assign("d.ub[%d]" % r, qp.ub[r])
-        for j in range(qp.nx):
-            em.assign("d.h[%d]" % j, qp.h[j])
-        out.append("  __device__ static __forceinline__ void eval_qp(%s, clik::QpData<Skill>& d) {" % sig)
+                em.assign("d.s[%d]" % j, dag.div(dag.ONE, dag.sqrt(qp.h[j])))
+            out.append("  __device__ static __forceinline__ void eval_qps(%s, clik::QpSData<Skill>& d) {" % sig)
+        else:
+            for r in range(qp.m):
+                for j in range(qp.nx):
+                    em.assign("d.A[%d]" % (r * qp.nx + j), qp.A[r][j])
+                em.assign("d.lb[%d]" % r, qp.lb[r])
+                em.assign("d.ub[%d]" % r, qp.ub[r])
+            for j in range(qp.nx):
+                em.assign("d.h[%d]" % j, qp.h[j])
+            out.append("  __device__ static __forceinline__ void eval_qp(%s, clik::QpData<Skill>& d) {" % sig)
         out += ["    " + ln for ln in em.finish()]
         out.append("  }")
         meta["qp_eval"] = em.counts()
@@ -511,7 +536,9 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
                        % (block_threads, int(os.environ.get("CLIK_STAGES", "2"))))
             out.append("}")
     if qp is not None:
-        out.append('extern "C" __global__ void __launch_bounds__(%d) clik_qp_kernel(' % block_threads)
+        qmin = int(os.environ.get("CLIK_QP_MINBLOCKS", "0"))
+        qbounds = "__launch_bounds__(%d%s)" % (block_threads, (", %d" % qmin) if qmin else "")
+        out.append('extern "C" __global__ void %s clik_qp_kernel(' % qbounds)
         out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
         out.append("    const double* y, const double* x0, double* sol, int* status, unsigned* active,")
         out.append("    int max_iter) {")

@@ -196,3 +196,12 @@ class QpProgram(object):
         self.m = len(self.A)
         nodes = self.h + self.lb + self.ub + [n for r in self.A for n in r]
         self.syms.check_closed(nodes, "QP matrices")
+        # row structure: a "unit" row has exactly one structural non-zero and it is a constant
+        # (bounds on a single variable: joint limits, speed limits); everything else is dense
+        self.unit_rows, self.dense_rows = [], []
+        for r, row in enumerate(self.A):
+            nz = [(j, n) for j, n in enumerate(row) if n is not dag.ZERO]
+            if len(nz) == 1 and nz[0][1].is_const and nz[0][1].val != 0.0:
+                self.unit_rows.append((r, nz[0][0], nz[0][1].val))
+            else:
+                self.dense_rows.append(r)

@@ -171,6 +171,281 @@ __device__ int qp_dual_active_set(const int nx, const int m, double* A, const do
   return status;
 }
 
+// ---- structured variant ---------------------------------------------------------------------------
+// Most rows of a reactive-QP are bounds on single variables (joint-position limits and joint-speed
+// limits are identity rows: reference reactive_qp.py:221-231 with expression = q), only the task
+// rows are dense.  The expression compiler classifies the rows at compile time (S::QMD dense rows,
+// S::QMU unit rows with constant coefficient S::unit_coef(i) on column S::unit_col(i)); this solver
+// runs the same Goldfarb-Idnani iteration as qp_dual_active_set but keeps the working set as
+//   * a set of fixed coordinates (active unit rows: their normals are coordinate vectors, so
+//     projecting them out is just "zero that coordinate"), and
+//   * a QR factorisation of the active dense normals restricted to the free coordinates,
+// which is at most QMD columns.  Everything is indexed at compile time and lives in registers.
+template <class S> struct QpSData {
+  double Ad[(S::QMD > 0 ? S::QMD : 1) * S::QN];   // dense rows (unscaled on entry)
+  double lbd[S::QMD > 0 ? S::QMD : 1], ubd[S::QMD > 0 ? S::QMD : 1];
+  double lbu[S::QMU > 0 ? S::QMU : 1], ubu[S::QMU > 0 ? S::QMU : 1];
+  double s[S::QN];                                 // 1 / sqrt(h_j)
+};
+
+template <class S>
+__device__ __forceinline__ int qp_structured(QpSData<S>& D, double (&x)[S::QN], unsigned* act_up,
+                                             unsigned* act_lo, const int max_iter) {
+  constexpr int NX = S::QN, MD = S::QMD, MU = S::QMU;
+  constexpr int MD1 = MD > 0 ? MD : 1, MU1 = MU > 0 ? MU : 1;
+  double z[NX], nF[NX], inF[NX], uF[NX];   // nF[j] != 0: coordinate j is fixed (entry of its normal; inF = 1/nF)
+  int frow[NX], fside[NX];           // active unit row on coordinate j and the side it is held at
+  double Qd[MD1 * NX], Rd[MD1 * MD1], iRd[MD1], uD[MD1], ks[MU1];   // iRd = 1 / diagonal of Rd
+  int ad[MD1];                       // 0 inactive, +1 held at upper, -1 held at lower
+  int nact = 0;
+#pragma unroll
+  for (int j = 0; j < NX; ++j) { z[j] = 0.0; nF[j] = 0.0; inF[j] = 0.0; uF[j] = 0.0; frow[j] = -1; fside[j] = 0; }
+#pragma unroll
+  for (int a = 0; a < MD; ++a) {
+    ad[a] = 0; uD[a] = 0.0; iRd[a] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) D.Ad[a * NX + j] *= D.s[j];
+  }
+#pragma unroll
+  for (int i = 0; i < MU; ++i) ks[i] = S::unit_coef(i) * D.s[S::unit_col(i)];
+
+  // QR of the active dense normals on the free coordinates, rebuilt in slot order
+  auto refactor = [&]() {
+#pragma unroll
+    for (int a = 0; a < MD; ++a) {
+      if (ad[a] != 0) {
+        double col[NX];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) col[j] = (nF[j] != 0.0) ? 0.0 : (double)ad[a] * D.Ad[a * NX + j];
+#pragma unroll
+        for (int l = 0; l < a; ++l) Rd[l * MD1 + a] = 0.0;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+          for (int l = 0; l < a; ++l) {
+            if (ad[l] != 0) {
+              double dt = 0.0;
+#pragma unroll
+              for (int j = 0; j < NX; ++j) dt = fma(Qd[l * NX + j], col[j], dt);
+#pragma unroll
+              for (int j = 0; j < NX; ++j) col[j] = fma(-dt, Qd[l * NX + j], col[j]);
+              Rd[l * MD1 + a] += dt;
+            }
+          }
+        }
+        double nrm = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) nrm = fma(col[j], col[j], nrm);
+        nrm = sqrt(nrm);
+        Rd[a * MD1 + a] = nrm;
+        const double inv = 1.0 / nrm;
+        iRd[a] = inv;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) Qd[a * NX + j] = col[j] * inv;
+      }
+    }
+  };
+
+  int status = QP_MAXITER;
+  for (int it = 0; it < max_iter; ++it) {
+    // ---- most violated one-sided constraint (same rule and tolerances as the dense solver) ----
+    int p = -1;            // 0..MD-1: dense slot, MD..MD+MU-1: unit row
+    double sp = 0.0, vbest = 0.0;
+#pragma unroll
+    for (int a = 0; a < MD; ++a) {
+      if (ad[a] == 0) {
+        double r = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) r = fma(D.Ad[a * NX + j], z[j], r);
+        const double vu = r - D.ubd[a], vl = D.lbd[a] - r;
+        const double tu = 1e-12 * fmax(1.0, fabs(D.ubd[a])), tl = 1e-12 * fmax(1.0, fabs(D.lbd[a]));
+        if (vu > tu && vu > vbest) { vbest = vu; p = a; sp = 1.0; }
+        if (vl > tl && vl > vbest) { vbest = vl; p = a; sp = -1.0; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MU; ++i) {
+      if (frow[S::unit_col(i)] != i) {
+        const double r = ks[i] * z[S::unit_col(i)];
+        const double vu = r - D.ubu[i], vl = D.lbu[i] - r;
+        const double tu = 1e-12 * fmax(1.0, fabs(D.ubu[i])), tl = 1e-12 * fmax(1.0, fabs(D.lbu[i]));
+        if (vu > tu && vu > vbest) { vbest = vu; p = MD + i; sp = 1.0; }
+        if (vl > tl && vl > vbest) { vbest = vl; p = MD + i; sp = -1.0; }
+      }
+    }
+    if (p < 0) { status = QP_OK; break; }
+
+    // ---- its normal -------------------------------------------------------------------------------
+    double np_[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) np_[j] = 0.0;
+#pragma unroll
+    for (int a = 0; a < MD; ++a) {
+      if (p == a) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) np_[j] = sp * D.Ad[a * NX + j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MU; ++i) {
+      if (p == MD + i) np_[S::unit_col(i)] = sp * ks[i];
+    }
+    double nn = 0.0;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) nn = fma(np_[j], np_[j], nn);
+
+    double up = 0.0;
+    bool done = false, infeasible = false;
+    while (!done) {
+      // ---- d = projection of n_p onto the null space of the working set, r = dual direction ------
+      double d[NX], cd[MD1], rd[MD1], rF[NX];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) d[j] = (nF[j] != 0.0) ? 0.0 : np_[j];
+#pragma unroll
+      for (int a = 0; a < MD; ++a) cd[a] = 0.0;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int a = 0; a < MD; ++a) {
+          if (ad[a] != 0) {
+            double dt = 0.0;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) dt = fma(Qd[a * NX + j], d[j], dt);
+#pragma unroll
+            for (int j = 0; j < NX; ++j) d[j] = fma(-dt, Qd[a * NX + j], d[j]);
+            cd[a] += dt;
+          }
+        }
+      }
+#pragma unroll
+      for (int a = MD - 1; a >= 0; --a) {
+        double acc = cd[a];
+#pragma unroll
+        for (int l = a + 1; l < MD; ++l) {
+          if (ad[l] != 0) acc = fma(-Rd[a * MD1 + l], rd[l], acc);
+        }
+        rd[a] = (ad[a] != 0) ? acc * iRd[a] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        double acc = np_[j];
+#pragma unroll
+        for (int a = 0; a < MD; ++a) {
+          if (ad[a] != 0) acc = fma(-(double)ad[a] * D.Ad[a * NX + j], rd[a], acc);
+        }
+        rF[j] = (nF[j] != 0.0) ? acc * inF[j] : 0.0;
+      }
+      double dn = 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) dn = fma(d[j], d[j], dn);
+      // ---- step lengths -----------------------------------------------------------------------------
+      double rmax = 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) rmax = fmax(rmax, fabs(rF[j]));
+#pragma unroll
+      for (int a = 0; a < MD; ++a) rmax = fmax(rmax, fabs(rd[a]));
+      // ratio test min u/r over r > 0, compared by cross-multiplication (one division at the end)
+      double ub_ = 0.0, rb_ = 0.0;
+      int drop = -1;       // 0..NX-1: release coordinate, NX..NX+MD-1: dense slot
+#pragma unroll
+      for (int a = 0; a < MD; ++a) {
+        if (ad[a] != 0 && rd[a] > 1e-12 * rmax && rd[a] > 0.0) {
+          if (drop < 0 || uD[a] * rb_ < ub_ * rd[a]) { ub_ = uD[a]; rb_ = rd[a]; drop = NX + a; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        if (nF[j] != 0.0 && rF[j] > 1e-12 * rmax && rF[j] > 0.0) {
+          if (drop < 0 || uF[j] * rb_ < ub_ * rF[j]) { ub_ = uF[j]; rb_ = rF[j]; drop = j; }
+        }
+      }
+      const double t1 = (drop >= 0) ? ub_ / rb_ : INFINITY;
+      double viol = 0.0;
+#pragma unroll
+      for (int a = 0; a < MD; ++a) {
+        if (p == a) {
+          double r = 0.0;
+#pragma unroll
+          for (int j = 0; j < NX; ++j) r = fma(D.Ad[a * NX + j], z[j], r);
+          viol = (sp > 0.0) ? (r - D.ubd[a]) : (D.lbd[a] - r);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < MU; ++i) {
+        if (p == MD + i) {
+          const double r = ks[i] * z[S::unit_col(i)];
+          viol = (sp > 0.0) ? (r - D.ubu[i]) : (D.lbu[i] - r);
+        }
+      }
+      const bool independent = (nact < NX) && (dn > 1e-24 * nn);
+      const double t2 = independent ? viol / dn : INFINITY;
+      const double t = fmin(t1, t2);
+      if (!(t < INFINITY)) { infeasible = true; break; }
+      if (independent) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) z[j] = fma(-t, d[j], z[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < NX; ++j) uF[j] = fma(-t, rF[j], uF[j]);
+#pragma unroll
+      for (int a = 0; a < MD; ++a) uD[a] = fma(-t, rd[a], uD[a]);
+      up += t;
+      if (t2 <= t1) {
+        // full step: p joins the working set
+#pragma unroll
+        for (int a = 0; a < MD; ++a) {
+          if (p == a) { ad[a] = (sp > 0.0) ? 1 : -1; uD[a] = up; }
+        }
+#pragma unroll
+        for (int i = 0; i < MU; ++i) {
+          if (p == MD + i) {
+            nF[S::unit_col(i)] = sp * ks[i];
+            inF[S::unit_col(i)] = 1.0 / (sp * ks[i]);
+            uF[S::unit_col(i)] = up;
+            frow[S::unit_col(i)] = i;
+            fside[S::unit_col(i)] = (sp > 0.0) ? 1 : -1;
+          }
+        }
+        ++nact;
+        done = true;
+      } else {
+        // partial step: release the blocking constraint, try again with the same p
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+          if (drop == j) { nF[j] = 0.0; inF[j] = 0.0; uF[j] = 0.0; frow[j] = -1; fside[j] = 0; }
+        }
+#pragma unroll
+        for (int a = 0; a < MD; ++a) {
+          if (drop == NX + a) { ad[a] = 0; uD[a] = 0.0; }
+        }
+        --nact;
+      }
+      refactor();
+    }
+    if (infeasible) { status = QP_INFEASIBLE; break; }
+  }
+
+#pragma unroll
+  for (int j = 0; j < NX; ++j) x[j] = z[j] * D.s[j];
+  unsigned mu = 0u, ml = 0u;
+#pragma unroll
+  for (int a = 0; a < MD; ++a) {
+    if (S::dense_row(a) < 32) {
+      if (ad[a] > 0) mu |= 1u << S::dense_row(a);
+      if (ad[a] < 0) ml |= 1u << S::dense_row(a);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MU; ++i) {
+    if (S::unit_row(i) < 32 && frow[S::unit_col(i)] == i) {
+      if (fside[S::unit_col(i)] > 0) mu |= 1u << S::unit_row(i); else ml |= 1u << S::unit_row(i);
+    }
+  }
+  *act_up = mu;
+  *act_lo = ml;
+  return status;
+}
+
 // Everything S::eval_qp produces for one instance.
 template <class S> struct QpData {
   double A[S::QM * S::QN];
@@ -197,16 +472,20 @@ __device__ __forceinline__ void qp_step(long long N, const double* __restrict__ 
     for (int j = 0; j < S::NX; ++j) xv[j] = __ldcs(x + (long long)j * N + i);
 #pragma unroll
     for (int j = 0; j < S::NY; ++j) yv[j] = __ldcs(y + (long long)j * N + i);
-    QpData<S> d;
-    S::eval_qp(tv, qv, xv, yv, d);
-    double x0v[S::QN], xs[S::QN];
-    if (x0 != nullptr) {
-      for (int j = 0; j < S::QN; ++j) x0v[j] = x0[(long long)j * N + i];
-    }
+    double xs[S::QN];
     unsigned mu, ml;
-    const int st = qp_dual_active_set<S::QN, S::QM>(S::QN, S::QM, d.A, d.lb, d.ub, d.h,
-                                                    x0 != nullptr ? x0v : nullptr, xs, &mu, &ml,
-                                                    max_iter);
+    int st;
+    if constexpr (S::QSTRUCT) {
+      // the dual method restarts from z = 0: x0 (primal warm start) does not change the answer
+      QpSData<S> d;
+      S::eval_qps(tv, qv, xv, yv, d);
+      st = qp_structured<S>(d, xs, &mu, &ml, max_iter);
+    } else {
+      QpData<S> d;
+      S::eval_qp(tv, qv, xv, yv, d);
+      st = qp_dual_active_set<S::QN, S::QM>(S::QN, S::QM, d.A, d.lb, d.ub, d.h, nullptr, xs, &mu, &ml,
+                                            max_iter);
+    }
     for (int j = 0; j < S::QN; ++j) __stcs(sol + (long long)j * N + i, xs[j]);
     if (status != nullptr) status[i] = st;
     if (active != nullptr) {
@@ -238,11 +517,18 @@ __device__ __forceinline__ void qp_rollout(long long N, int steps, double dt, co
     int failed = 0;
     for (int k = 0; k < steps; ++k) {
       const double tv = __dadd_rn(t0v, __dmul_rn(dt, (double)k));
-      QpData<S> d;
-      S::eval_qp(tv, qv, xv, yv, d);
       unsigned mu, ml;
-      const int st = qp_dual_active_set<S::QN, S::QM>(S::QN, S::QM, d.A, d.lb, d.ub, d.h, nullptr, xs,
-                                                      &mu, &ml, max_iter);
+      int st;
+      if constexpr (S::QSTRUCT) {
+        QpSData<S> d;
+        S::eval_qps(tv, qv, xv, yv, d);
+        st = qp_structured<S>(d, xs, &mu, &ml, max_iter);
+      } else {
+        QpData<S> d;
+        S::eval_qp(tv, qv, xv, yv, d);
+        st = qp_dual_active_set<S::QN, S::QM>(S::QN, S::QM, d.A, d.lb, d.ub, d.h, nullptr, xs, &mu, &ml,
+                                              max_iter);
+      }
       if (st != QP_OK) {
         ++failed;
         for (int j = 0; j < S::QN; ++j) xs[j] = 0.0;

@@ -137,3 +137,107 @@ def test_more_active_rows_than_variables_and_infeasible(host_qp):
     # 12 narrow bands in 6-D that exclude each other: both solvers must say infeasible
     _, st2, _, _ = host_qp(np.ones(6), A, r + 0.5, r + 1.0)
     assert st2 == orc.solve_qp_single(np.ones(6), A, r + 0.5, r + 1.0)[2] == 2
+
+
+# ---- structured (register-resident) variant ---------------------------------------------------------
+SHIM_S = SHIM.split('#include "%s"')[0] + r'''
+#include <cstring>
+#include "%s"
+struct S {
+  static constexpr int QN = 6, QMD = 2, QMU = 7, QM = 9;
+  static constexpr int dense_row(int a) { return a == 0 ? 1 : 4; }
+  static constexpr int unit_row(int i) { constexpr int t[7] = {0, 2, 3, 5, 6, 7, 8}; return t[i]; }
+  static constexpr int unit_col(int i) { constexpr int t[7] = {0, 1, 2, 0, 3, 5, 1}; return t[i]; }
+  static constexpr double unit_coef(int i) { constexpr double t[7] = {1.0, 1.0, -1.0, 2.0, 1.0, -0.5, 1.0}; return t[i]; }
+};
+extern "C" int host_qps(const double* Ad, const double* lbd, const double* ubd, const double* lbu,
+                        const double* ubu, const double* s, double* x, unsigned* au, unsigned* al, int max_iter) {
+  clik::QpSData<S> d;
+  std::memcpy(d.Ad, Ad, sizeof(d.Ad)); std::memcpy(d.lbd, lbd, sizeof(d.lbd)); std::memcpy(d.ubd, ubd, sizeof(d.ubd));
+  std::memcpy(d.lbu, lbu, sizeof(d.lbu)); std::memcpy(d.ubu, ubu, sizeof(d.ubu)); std::memcpy(d.s, s, sizeof(d.s));
+  double xs[S::QN];
+  int st = clik::qp_structured<S>(d, xs, au, al, max_iter);
+  for (int j = 0; j < S::QN; ++j) x[j] = xs[j];
+  return st;
+}
+'''
+DENSE_ROWS = [1, 4]
+UNIT = [(0, 0, 1.0), (2, 1, 1.0), (3, 2, -1.0), (5, 0, 2.0), (6, 3, 1.0), (7, 5, -0.5), (8, 1, 1.0)]   # (row, col, coef)
+
+
+@pytest.fixture(scope="module")
+def host_qps(tmp_path_factory):
+    d = tmp_path_factory.mktemp("qps_host")
+    src = d / "host_qps.cpp"
+    src.write_text(SHIM_S % os.path.join(ROOT, "casclik_b200", "csrc", "clik_qp.cuh"))
+    so = d / "host_qps.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", str(so), str(src)], check=True)
+    lib = ctypes.CDLL(str(so))
+
+    def solve(h, A, lb, ub, max_iter=400):
+        Ad = np.ascontiguousarray(A[DENSE_ROWS])
+        ur = [r for r, _, _ in UNIT]
+        arrs = [Ad, lb[DENSE_ROWS], ub[DENSE_ROWS], lb[ur], ub[ur], 1.0 / np.sqrt(h)]
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
+        x = np.zeros(6)
+        au, al = ctypes.c_uint(), ctypes.c_uint()
+        st = lib.host_qps(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs],
+                          x.ctypes.data_as(ctypes.c_void_p), ctypes.byref(au), ctypes.byref(al), max_iter)
+        return x, st, au.value, al.value
+    return solve
+
+
+def _structured_problem(rng, eq_prob=0.3, tight=False):
+    n, m = 6, 9
+    A = np.zeros((m, n))
+    A[DENSE_ROWS] = rng.normal(size=(2, n))
+    for r, c, k in UNIT:
+        A[r, c] = k
+    h = rng.uniform(0.001, 2.0, n)
+    x_in = rng.normal(size=n)
+    r = A @ x_in
+    w = 0.05 if tight else 1.0
+    lb, ub = r - rng.uniform(0, w, m), r + rng.uniform(0, w, m)
+    for i in range(m):
+        c = rng.random()
+        if c < 0.1:
+            lb[i] = -np.inf
+        elif c < 0.2:
+            ub[i] = np.inf
+        elif c < 0.3:
+            lb[i], ub[i] = -1e10, 1e10
+        elif c < 0.3 + 0.1 * eq_prob and i in DENSE_ROWS:
+            lb[i] = ub[i] = r[i]
+    return h, A, lb, ub
+
+
+def test_structured_solver_matches_oracle_and_dense_solver(host_qp, host_qps):
+    rng = np.random.default_rng(11)
+    for trial in range(400):
+        h, A, lb, ub = _structured_problem(rng, tight=(trial % 3 == 0))
+        x, st, au, al = host_qps(h, A, lb, ub)
+        xo, lamo, sto = orc.solve_qp_single(h, A, lb, ub)
+        xg, stg, aug, alg = host_qp(h, A, lb, ub)
+        assert st == sto == stg == 0, (trial, st, sto, stg)
+        kk = orc.kkt_residuals(h, A, lb, ub, x)
+        assert kk["primal"] < 1e-9 and kk["stationarity"] < 1e-9 and kk["sign"] < 1e-9, (trial, kk)
+        assert np.abs(x - xo).max() < 1e-9 * (1 + np.abs(xo).max()), trial
+        assert (au, al) == _masks(lamo) == (aug, alg), trial
+
+
+def test_structured_solver_infeasible_and_cap(host_qps):
+    rng = np.random.default_rng(2)
+    h, A, lb, ub = _structured_problem(rng)
+    lb2, ub2 = lb.copy(), ub.copy()
+    lb2[0], ub2[0] = 1.0, 2.0          # x0 in [1, 2]
+    lb2[5], ub2[5] = -8.0, -6.0        # 2*x0 in [-8, -6]  -> contradiction on the same coordinate
+    _, st, _, _ = host_qps(h, A, lb2, ub2)
+    assert st == 2 and orc.solve_qp_single(h, A, lb2, ub2)[2] == 2
+    lb3, ub3 = lb.copy(), ub.copy()
+    lb3[:] = np.where(np.isfinite(lb3), lb3, -50.0) + 3.0
+    ub3[:] = lb3 + 0.5
+    ok = orc.solve_qp_single(h, A, lb3, ub3)[2]
+    _, st3, _, _ = host_qps(h, A, lb3, ub3)
+    assert st3 == ok
+    _, st1, _, _ = host_qps(h, A, lb3, ub3, 1)
+    assert st1 in (1, 2)
