@@ -101,3 +101,18 @@ def compile_cubin(source: str, tag: str = "skill", keep_source=True, extra_flags
             os.remove(cu)
     with open(cubin, "rb") as f:
         return f.read(), cubin
+
+
+def kernel_registers(cubin_path, kernel):
+    """Registers per thread ptxas reported for `kernel` (from the compile log next to the cubin)."""
+    import re
+    log_path = cubin_path[:-len(".cubin")] + ".log"
+    if not os.path.exists(log_path):
+        return None
+    with open(log_path) as f:
+        log = f.read()
+    key = "Compiling entry function '%s'" % kernel
+    if key not in log:
+        return None
+    m = re.search(r"Used (\d+) registers", log[log.index(key):])
+    return int(m.group(1)) if m else None

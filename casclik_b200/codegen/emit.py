@@ -397,6 +397,14 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         ns_ = pinv.n_sets
         upto2 = 1 + ns_ + ns_ * (ns_ - 1) // 2
         default_static = len(masks) if len(masks) <= 8 else (upto2 if upto2 <= 64 else 1 + ns_)
+        unit_sets = pinv.unit_sets if os.environ.get("CLIK_UNIT_SETS", "1") == "1" else None
+        meta["pinv_unit_sets"] = bool(unit_sets)
+        out.append("  static constexpr bool UNIT_SETS = %s;   // every set bounds one coordinate: closed-form modes"
+                   % ("true" if unit_sets else "false"))
+        out.append(_switch("set_unit_col", [c for c, _ in (unit_sets or [(0, 1.0)])]))
+        out.append(_switch("set_unit_coef", [literal(k) for _, k in (unit_sets or [(0, 1.0)])], ret="double"))
+        if unit_sets:
+            default_static = 1
         n_static = int(os.environ.get("CLIK_NSTATIC", "0")) or default_static
         n_static = max(1, min(n_static, len(masks)))
         meta["pinv_static_modes"] = n_static
@@ -540,9 +548,9 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         qbounds = "__launch_bounds__(%d%s)" % (block_threads, (", %d" % qmin) if qmin else "")
         out.append('extern "C" __global__ void %s clik_qp_kernel(' % qbounds)
         out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
-        out.append("    const double* y, const double* x0, double* sol, int* status, unsigned* active,")
-        out.append("    int max_iter) {")
-        out.append("  clik::qp_step<Skill>(N, t, t_stride, q, x, y, x0, sol, status, active, max_iter);")
+        out.append("    const double* y, const double* x0, const unsigned* active0, double* sol, int* status,")
+        out.append("    unsigned* active, int max_iter) {")
+        out.append("  clik::qp_step<Skill>(N, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
         out.append("}")
     if qp is not None:
         out.append('extern "C" __global__ void __launch_bounds__(%d) clik_qp_rollout_kernel(' % block_threads)

@@ -126,6 +126,24 @@ class PinvProgram(object):
         self.m = row
         self.n_sets = set_idx
         self.max_rows = max(b["rows"] for b in self.blocks)
+        # "unit sets": every SetConstraint bounds a single state coordinate with a constant
+        # coefficient (joint limits: e = q_k), on distinct coordinates, and the only Eq / VelEq
+        # constraint comes after all of them.  Then the stacked active-set Jacobian has
+        # S S' = diag(c_k^2) and a mode's null-space projector is a per-coordinate scaling.
+        self.unit_sets = None
+        sets = [b for b in self.blocks if b["kind"] == KIND_SET]
+        tasks = [b for b in self.blocks if b["kind"] in (KIND_EQ, KIND_VELEQ)]
+        if sets and len(tasks) == 1 and self.blocks[-1] is tasks[0]:
+            info, cols = [], set()
+            for b in sets:
+                nz = [(j, n) for j, n in enumerate(b["J"][0]) if n is not dag.ZERO]
+                if len(nz) == 1 and nz[0][1].is_const and nz[0][1].val != 0.0 and nz[0][0] not in cols:
+                    cols.add(nz[0][0])
+                    info.append((nz[0][0], nz[0][1].val))
+                else:
+                    info = None
+                    break
+            self.unit_sets = info
         for b in self.blocks:
             nodes = b["e"] + b["jt"] + [n for r in b["J"] for n in r]
             nodes += b.get("des", []) + b.get("smin", []) + b.get("smax", [])

@@ -12,6 +12,8 @@ one CUDA translation unit for the skill (casclik_b200/codegen) and loads it thro
 Options are read when `setup_*` runs, not at construction, because the reference stores the dict
 by reference and the notebooks mutate it in between.
 """
+import os
+
 import numpy as np
 
 from .. import build, runtime
@@ -107,6 +109,13 @@ class PseudoInverseController(BaseController):
         prog = PinvProgram(self.skill_spec, self.options)
         source, meta = emit_skill(pinv=prog, label=self.skill_spec.label)
         cubin, path = build.compile_cubin(source, tag="pinv_" + self.skill_spec.label)
+        regs = build.kernel_registers(path, "clik_pinv_kernel")
+        if regs is not None and regs > 128 and "CLIK_MINBLOCKS" not in os.environ:
+            # large skills (7-DOF pose tasks, many sets) are latency-bound at 2 CTAs/SM: measured
+            # 1.7e9 -> 2.8e9 steps/s for the iiwa scenario with the register cap of 4 CTAs/SM
+            source, meta = emit_skill(pinv=prog, label=self.skill_spec.label, min_blocks=4)
+            cubin, path = build.compile_cubin(source, tag="pinv_" + self.skill_spec.label)
+            meta["register_cap"] = "launch_bounds(128, 4): natural allocation was %d" % regs
         self.kernel_source, self.kernel_meta, self.cubin_path = source, meta, path
         self._nx, self._ny = prog.n_virt, prog.n_in
         self._cubin = cubin

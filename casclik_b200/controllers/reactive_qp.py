@@ -206,9 +206,11 @@ class ReactiveQPController(BaseController):
 
     # ---- step --------------------------------------------------------------------------------------
     def solve_batch(self, time_var, robot_var, virtual_var=None, input_var=None, warmstart=None,
-                    out=None, max_iter=None):
+                    out=None, max_iter=None, warm_active=None):
         """QP controller step for N instances (same layout rules as
-        PseudoInverseController.solve_batch).  warmstart: optional (nx, N) primal guess.
+        PseudoInverseController.solve_batch).  warmstart: optional (nx, N) primal guess;
+        warm_active: optional (2, N) int32 working-set guess in the format of the returned `active`
+        (e.g. the previous step's).  Either only shortens the active-set iteration.
         Returns (sol (nx, N), status (N,) int32, active (2, N) int32 bit masks [upper; lower]);
         rows of `sol` are [robot vel; virtual vel; slack]."""
         skill = self._skill()
@@ -227,15 +229,21 @@ class ReactiveQPController(BaseController):
                 x0p = runtime.dev_ptr(warmstart, "f64", self._qn * b.N, "warmstart")
             else:
                 x0p, warmstart = runtime.host_ptr(warmstart, np.float64, self._qn * b.N, "warmstart")
+        a0p = None
+        if warm_active is not None:
+            if b.on_device:
+                a0p = runtime.dev_ptr(warm_active, "u32", 2 * b.N, "warm_active")
+            else:
+                a0p, warm_active = runtime.host_ptr(warm_active, np.int32, 2 * b.N, "warm_active")
         mi = int(max_iter if max_iter is not None else self.options.get("max_iter", 0) or 0)
         lib = runtime.load_library()
         if b.on_device:
             runtime.check(lib.clik_qp_step(skill.handle, b.N, b.tp, b.t_stride, b.qp, b.xp, b.yp,
-                                           x0p, b.ptr(sol), b.ptr(status), b.ptr(active), mi,
+                                           x0p, a0p, b.ptr(sol), b.ptr(status), b.ptr(active), mi,
                                            b.stream()))
         else:
             runtime.check(lib.clik_qp_step_host(skill.handle, b.N, b.tp, b.t_stride, b.qp, b.xp,
-                                                b.yp, x0p, b.ptr(sol), b.ptr(status),
+                                                b.yp, x0p, a0p, b.ptr(sol), b.ptr(status),
                                                 b.ptr(active), mi))
         return sol, status, active
 

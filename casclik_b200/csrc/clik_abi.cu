@@ -435,8 +435,8 @@ clik_status clik_pinv_rollout(const clik_skill* s, int64_t N, int32_t steps, dou
 
 clik_status clik_qp_step(const clik_skill* s, int64_t N, const double* t, int32_t t_stride,
                          const double* q, const double* x, const double* y, const double* x0,
-                         double* sol, int32_t* status, uint32_t* active, int32_t max_iter,
-                         void* stream) {
+                         const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
+                         int32_t max_iter, void* stream) {
   clik_status st = check_common(s, N, t, q, x, y);
   if (st != CLIK_OK || N == 0) return st;
   if (!s->qp.kernel) return fail(CLIK_ERR_INVALID, "skill was built without the QP kernel");
@@ -445,7 +445,7 @@ clik_status clik_qp_step(const clik_skill* s, int64_t N, const double* t, int32_
   long long n = N;
   int ts = t_stride ? 1 : 0;
   int mi = max_iter > 0 ? max_iter : 10 * (s->desc.qp_n + s->desc.qp_m);
-  void* args[] = {&n, &t, &ts, &q, &x, &y, &x0, &sol, &status, &active, &mi};
+  void* args[] = {&n, &t, &ts, &q, &x, &y, &x0, &active0, &sol, &status, &active, &mi};
   CK(cudaLaunchKernel((const void*)s->qp.kernel, dim3(grid_for(s->qp, N)), dim3(s->qp.block), args,
                       0, (cudaStream_t)stream));
   return CLIK_OK;
@@ -524,7 +524,8 @@ clik_status clik_pinv_step_host(const clik_skill* cs, int64_t N, const double* t
 
 clik_status clik_qp_step_host(const clik_skill* cs, int64_t N, const double* t, int32_t t_stride,
                               const double* q, const double* x, const double* y, const double* x0,
-                              double* sol, int32_t* status, uint32_t* active, int32_t max_iter) {
+                              const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
+                              int32_t max_iter) {
   clik_skill* s = const_cast<clik_skill*>(cs);
   clik_status st = check_common(s, N, t, q, x, y);
   if (st != CLIK_OK || N == 0) return st;
@@ -543,12 +544,14 @@ clik_status clik_qp_step_host(const clik_skill* cs, int64_t N, const double* t, 
   f.push_back({nullptr, sol, d.qp_n, 8, 1, 0});
   f.push_back({nullptr, status, 1, 4, 1, 0});
   f.push_back({nullptr, active, 2, 4, 1, 0});
+  f.push_back({active0, nullptr, 2, 4, 1, 0});
   return run_host_pipeline(s, N, f, [&](char* base, int64_t c, cudaStream_t stream) {
     return clik_qp_step(s, c, (const double*)(base + f[0].dev_off), t_stride,
                         (const double*)(base + f[1].dev_off),
                         d.n_virtual ? (const double*)(base + f[2].dev_off) : nullptr,
                         d.n_input ? (const double*)(base + f[3].dev_off) : nullptr,
                         x0 ? (const double*)(base + f[4].dev_off) : nullptr,
+                        active0 ? (const uint32_t*)(base + f[8].dev_off) : nullptr,
                         (double*)(base + f[5].dev_off),
                         status ? (int32_t*)(base + f[6].dev_off) : nullptr,
                         active ? (uint32_t*)(base + f[7].dev_off) : nullptr, max_iter, stream);

@@ -520,6 +520,46 @@ __device__ __noinline__ bool dynamic_mode(const PinvData<S>* d, const TaskVel<S>
 // ---- the step --------------------------------------------------------------------------------------
 // One instance, inputs already in registers: evaluate the skill, try mode 0 on the static path,
 // fall back to the run-time mode search, and return the accepted mode index (-1: none).
+// Mode with run-time mask for skills whose SetConstraints each bound one state coordinate with a
+// constant coefficient (S::UNIT_SETS: joint limits, e = c*q_k) and whose single Eq / VelEq task has
+// the lowest priority.  With at least one active set the task is not "first", so
+// v = (I - S'(S S' + lam I)^-1 S) w with S S' = diag(c_k^2): the projector only rescales the active
+// coordinates.  Same operations, in the same order, as the generic path performs on such rows
+// (b = c w_k; Cholesky of the 1x1 block c^2 + lam via rsqrt; two substitutions; w_k - c z).
+template <class S>
+__device__ __forceinline__ bool unit_set_mode(const PinvData<S>& d, const TaskVel<S>& tw, unsigned mask,
+                                              double (&v)[S::NS]) {
+  constexpr double lam = S::DAMPED ? S::LAMBDA : 0.0;
+#pragma unroll
+  for (int j = 0; j < S::NS; ++j) v[j] = tw.w[0][j];
+#pragma unroll
+  for (int c = 0; c < S::NC; ++c) {
+    if (S::kind(c) == KIND_SET) {
+      const int k = S::set_index(c);
+      const int col = S::set_unit_col(k);
+      const double coef = S::set_unit_coef(k);
+      if ((mask >> k) & 1u) {
+        const double r = rsqrt(coef * coef + lam);
+        const double zk = ((coef * v[col]) * r) * r;
+        v[col] = v[col] - coef * zk;
+      }
+    }
+  }
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < S::NC; ++c) {
+    if (S::kind(c) == KIND_SET) {
+      const int k = S::set_index(c);
+      if (!((mask >> k) & 1u)) {
+        const int r = S::row0(c);
+        const double de = d.jt[r] + S::set_unit_coef(k) * v[S::set_unit_col(k)];
+        ok = ok && in_tangent_cone(d.e[r], de, d.smin[r], d.smax[r]);
+      }
+    }
+  }
+  return ok;
+}
+
 // Run-time mode index -> statically instantiated mode (the first S::NSTATIC entries of the
 // activation map: mode 0 and the single-set modes, or every mode when there are at most 8).
 template <class S, int MI> struct StaticDispatch {
@@ -552,6 +592,20 @@ __device__ __forceinline__ int solve_instance(const double tv, const double (&qv
     if constexpr (PRE) compute_task_vel<S>(d, tw);
     if (static_mode<S, 0u, PRE>(d, tw, v)) return 0;
     int accepted = -1;
+    if constexpr (S::UNIT_SETS) {
+      // closed-form modes in registers: no static instantiations, no local-memory path
+      for (int mi = 1; mi < S::NMODES; ++mi) {
+        if (unit_set_mode<S>(d, tw, S::mode_mask(mi), v)) {
+          accepted = mi;
+          break;
+        }
+      }
+      if (accepted < 0) {
+#pragma unroll
+        for (int j = 0; j < S::NS; ++j) v[j] = 0.0;
+      }
+      return accepted;
+    }
     for (int mi = 1; mi < S::NSTATIC; ++mi) {
       if (StaticDispatch<S, 1 < S::NSTATIC ? 1 : 0>::run(mi, d, tw, v)) {
         accepted = mi;

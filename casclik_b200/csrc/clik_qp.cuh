@@ -188,9 +188,16 @@ template <class S> struct QpSData {
   double s[S::QN];                                 // 1 / sqrt(h_j)
 };
 
+// warm_up / warm_lo (optional, 0 = cold start): a guess of the final working set in the output
+// format (bit r = original row r held at its upper / lower bound), e.g. the previous step's masks
+// in a closed-loop rollout.  The guess is turned into a valid dual-feasible starting point (minimum-
+// norm point on the guessed face, constraints with negative multipliers released, equality rows
+// flipped to the side with a positive multiplier); the iteration then proceeds as usual, so the
+// result does not depend on the guess.
 template <class S>
 __device__ __forceinline__ int qp_structured(QpSData<S>& D, double (&x)[S::QN], unsigned* act_up,
-                                             unsigned* act_lo, const int max_iter) {
+                                             unsigned* act_lo, const int max_iter,
+                                             const unsigned warm_up = 0u, const unsigned warm_lo = 0u) {
   constexpr int NX = S::QN, MD = S::QMD, MU = S::QMU;
   constexpr int MD1 = MD > 0 ? MD : 1, MU1 = MU > 0 ? MU : 1;
   double z[NX], nF[NX], inF[NX], uF[NX];   // nF[j] != 0: coordinate j is fixed (entry of its normal; inF = 1/nF)
@@ -245,6 +252,123 @@ __device__ __forceinline__ int qp_structured(QpSData<S>& D, double (&x)[S::QN], 
       }
     }
   };
+
+  if ((warm_up | warm_lo) != 0u) {
+    // ---- adopt the guessed working set ---------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < MU; ++i) {
+      const bool up_ = S::unit_row(i) < 32 && ((warm_up >> S::unit_row(i)) & 1u);
+      const bool lo_ = S::unit_row(i) < 32 && ((warm_lo >> S::unit_row(i)) & 1u);
+      const double bnd = up_ ? D.ubu[i] : D.lbu[i];
+      if ((up_ || lo_) && frow[S::unit_col(i)] < 0 && nact < NX && (fabs(bnd) < INFINITY)) {
+        const double sgn = up_ ? 1.0 : -1.0;
+        nF[S::unit_col(i)] = sgn * ks[i];
+        inF[S::unit_col(i)] = 1.0 / (sgn * ks[i]);
+        frow[S::unit_col(i)] = i;
+        fside[S::unit_col(i)] = up_ ? 1 : -1;
+        z[S::unit_col(i)] = bnd / ks[i];
+        ++nact;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < MD; ++a) {
+      const bool up_ = S::dense_row(a) < 32 && ((warm_up >> S::dense_row(a)) & 1u);
+      const bool lo_ = S::dense_row(a) < 32 && ((warm_lo >> S::dense_row(a)) & 1u);
+      const double bnd = up_ ? D.ubd[a] : D.lbd[a];
+      if ((up_ || lo_) && nact < NX && (fabs(bnd) < INFINITY)) { ad[a] = up_ ? 1 : -1; ++nact; }
+    }
+    // release / flip until every multiplier is non-negative
+    bool warm_ok = false;
+    for (int round = 0; round <= 2 * NX + MD; ++round) {
+      refactor();
+      // a dense row that became dependent on the rest of the guess is dropped
+      bool dropped = false;
+#pragma unroll
+      for (int a = 0; a < MD; ++a) {
+        if (ad[a] != 0 && !(Rd[a * MD1 + a] > 1e-12)) { ad[a] = 0; --nact; dropped = true; }
+      }
+      if (dropped) continue;
+      // minimum-norm point on the face: fixed coordinates at their bounds, free part = Qd Rd^-T rhs
+      double y[MD1], ud[MD1];
+#pragma unroll
+      for (int a = 0; a < MD; ++a) {
+        double rhs = (ad[a] > 0) ? D.ubd[a] : -D.lbd[a];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+          if (nF[j] != 0.0) rhs = fma(-(double)ad[a] * D.Ad[a * NX + j], z[j], rhs);
+        }
+#pragma unroll
+        for (int l = 0; l < a; ++l) {
+          if (ad[l] != 0) rhs = fma(-Rd[l * MD1 + a], y[l], rhs);
+        }
+        y[a] = (ad[a] != 0) ? rhs * iRd[a] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        if (nF[j] == 0.0) {
+          double acc = 0.0;
+#pragma unroll
+          for (int a = 0; a < MD; ++a) {
+            if (ad[a] != 0) acc = fma(Qd[a * NX + j], y[a], acc);
+          }
+          z[j] = acc;
+        }
+      }
+      // multipliers from z + N u = 0
+#pragma unroll
+      for (int a = MD - 1; a >= 0; --a) {
+        double acc = -y[a];
+#pragma unroll
+        for (int l = a + 1; l < MD; ++l) {
+          if (ad[l] != 0) acc = fma(-Rd[a * MD1 + l], ud[l], acc);
+        }
+        ud[a] = (ad[a] != 0) ? acc * iRd[a] : 0.0;
+      }
+      // equality rows with a negative multiplier are simply held from the other side
+      bool flipped = false;
+#pragma unroll
+      for (int a = 0; a < MD; ++a) {
+        uD[a] = ud[a];
+        if (ad[a] != 0 && ud[a] < 0.0 && D.lbd[a] == D.ubd[a]) { ad[a] = -ad[a]; flipped = true; }
+      }
+      if (flipped) continue;                     // recompute with the new signs
+      double worst = 0.0;
+      int wi = -1;          // 0..NX-1 coordinate, NX.. dense slot
+#pragma unroll
+      for (int a = 0; a < MD; ++a) {
+        if (ad[a] != 0 && ud[a] < worst) { worst = ud[a]; wi = NX + a; }
+      }
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        if (nF[j] != 0.0) {
+          double acc = z[j];
+#pragma unroll
+          for (int a = 0; a < MD; ++a) {
+            if (ad[a] != 0) acc = fma((double)ad[a] * D.Ad[a * NX + j], ud[a], acc);
+          }
+          uF[j] = -acc * inF[j];
+          if (uF[j] < worst) { worst = uF[j]; wi = j; }
+        }
+      }
+      if (wi == -1) { warm_ok = true; break; }   // dual feasible: done
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        if (wi == j) { nF[j] = 0.0; inF[j] = 0.0; uF[j] = 0.0; frow[j] = -1; fside[j] = 0; z[j] = 0.0; }
+      }
+#pragma unroll
+      for (int a = 0; a < MD; ++a) {
+        if (wi == NX + a) { ad[a] = 0; uD[a] = 0.0; }
+      }
+      --nact;
+    }
+    if (!warm_ok) {                              // could not repair the guess: cold start
+      nact = 0;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) { z[j] = 0.0; nF[j] = 0.0; inF[j] = 0.0; uF[j] = 0.0; frow[j] = -1; fside[j] = 0; }
+#pragma unroll
+      for (int a = 0; a < MD; ++a) { ad[a] = 0; uD[a] = 0.0; }
+    }
+  }
 
   int status = QP_MAXITER;
   for (int it = 0; it < max_iter; ++it) {
@@ -446,6 +570,34 @@ __device__ __forceinline__ int qp_structured(QpSData<S>& D, double (&x)[S::QN], 
   return status;
 }
 
+// Working-set guess from a primal guess x0 (the reference's `x0=` warm start, reactive_qp.py:495-513):
+// rows whose value at x0 sits on one of their bounds (relative 1e-9), plus every equality row.
+template <class S>
+__device__ __forceinline__ void masks_from_x0(const QpSData<S>& D, const double (&x0)[S::QN], unsigned* up,
+                                              unsigned* lo) {
+  unsigned mu = 0u, ml = 0u;
+#pragma unroll
+  for (int a = 0; a < S::QMD; ++a) {
+    double r = 0.0;
+#pragma unroll
+    for (int j = 0; j < S::QN; ++j) r = fma(D.Ad[a * S::QN + j], x0[j], r);   // Ad still unscaled here
+    if (S::dense_row(a) < 32) {
+      if (D.lbd[a] == D.ubd[a] || fabs(r - D.ubd[a]) <= 1e-9 * (1.0 + fabs(D.ubd[a]))) mu |= 1u << S::dense_row(a);
+      else if (fabs(r - D.lbd[a]) <= 1e-9 * (1.0 + fabs(D.lbd[a]))) ml |= 1u << S::dense_row(a);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < S::QMU; ++i) {
+    const double r = S::unit_coef(i) * x0[S::unit_col(i)];
+    if (S::unit_row(i) < 32) {
+      if (fabs(r - D.ubu[i]) <= 1e-9 * (1.0 + fabs(D.ubu[i]))) mu |= 1u << S::unit_row(i);
+      else if (fabs(r - D.lbu[i]) <= 1e-9 * (1.0 + fabs(D.lbu[i]))) ml |= 1u << S::unit_row(i);
+    }
+  }
+  *up = mu;
+  *lo = ml;
+}
+
 // Everything S::eval_qp produces for one instance.
 template <class S> struct QpData {
   double A[S::QM * S::QN];
@@ -460,8 +612,8 @@ template <class S>
 __device__ __forceinline__ void qp_step(long long N, const double* __restrict__ t, int t_stride,
                                         const double* __restrict__ q, const double* __restrict__ x,
                                         const double* __restrict__ y, const double* __restrict__ x0,
-                                        double* __restrict__ sol, int* __restrict__ status,
-                                        unsigned* __restrict__ active, int max_iter) {
+                                        const unsigned* active0, double* __restrict__ sol,
+                                        int* __restrict__ status, unsigned* active, int max_iter) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
     double qv[S::NQ > 0 ? S::NQ : 1], xv[S::NX > 0 ? S::NX : 1], yv[S::NY > 0 ? S::NY : 1];
@@ -479,7 +631,28 @@ __device__ __forceinline__ void qp_step(long long N, const double* __restrict__ 
       // the dual method restarts from z = 0: x0 (primal warm start) does not change the answer
       QpSData<S> d;
       S::eval_qps(tv, qv, xv, yv, d);
-      st = qp_structured<S>(d, xs, &mu, &ml, max_iter);
+      // warm start: an explicit working-set guess (active0, may alias `active`) wins over one
+      // derived from the primal guess x0; neither changes the answer, only the iteration count
+      unsigned wu = 0u, wl = 0u;
+      if (active0 != nullptr) {
+        wu = active0[i];
+        wl = active0[N + i];
+      } else if (x0 != nullptr) {
+        double x0v[S::QN];
+#pragma unroll
+        for (int j = 0; j < S::QN; ++j) x0v[j] = x0[(long long)j * N + i];
+        masks_from_x0<S>(d, x0v, &wu, &wl);
+      }
+      st = QP_MAXITER;
+#pragma unroll 1
+      for (int attempt = 0; attempt < 2; ++attempt) {   // a bad guess must never cost the answer:
+        if (attempt > 0) {                              // second attempt = cold start
+          wu = wl = 0u;
+          S::eval_qps(tv, qv, xv, yv, d);
+        }
+        st = qp_structured<S>(d, xs, &mu, &ml, max_iter, wu, wl);
+        if (st == QP_OK || (wu | wl) == 0u) break;
+      }
     } else {
       QpData<S> d;
       S::eval_qp(tv, qv, xv, yv, d);
@@ -515,14 +688,24 @@ __device__ __forceinline__ void qp_rollout(long long N, int steps, double dt, co
     double xs[S::QN];
     for (int j = 0; j < S::QN; ++j) xs[j] = 0.0;
     int failed = 0;
+    unsigned mu = 0u, ml = 0u;        // working set of the previous step = warm start of the next
     for (int k = 0; k < steps; ++k) {
       const double tv = __dadd_rn(t0v, __dmul_rn(dt, (double)k));
-      unsigned mu, ml;
       int st;
       if constexpr (S::QSTRUCT) {
         QpSData<S> d;
         S::eval_qps(tv, qv, xv, yv, d);
-        st = qp_structured<S>(d, xs, &mu, &ml, max_iter);
+        unsigned wu = mu, wl = ml;
+        st = QP_MAXITER;
+#pragma unroll 1
+        for (int attempt = 0; attempt < 2; ++attempt) {
+          if (attempt > 0) {
+            wu = wl = 0u;
+            S::eval_qps(tv, qv, xv, yv, d);
+          }
+          st = qp_structured<S>(d, xs, &mu, &ml, max_iter, wu, wl);
+          if (st == QP_OK || (wu | wl) == 0u) break;
+        }
       } else {
         QpData<S> d;
         S::eval_qp(tv, qv, xv, yv, d);

@@ -78,9 +78,9 @@ def load_library():
     lib.clik_qp_rollout.argtypes = [vp, i64, i32, ctypes.c_double, vp, i32, vp, vp, vp,
                                     ctypes.c_double, ctypes.c_double, vp, vp, i32, vp]
     lib.clik_qp_step.restype = i32
-    lib.clik_qp_step.argtypes = [vp, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]
+    lib.clik_qp_step.argtypes = [vp, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.clik_qp_step_host.restype = i32
-    lib.clik_qp_step_host.argtypes = [vp, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32]
+    lib.clik_qp_step_host.argtypes = [vp, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32]
     lib.clik_qp_dense.restype = i32
     lib.clik_qp_dense.argtypes = [i32, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.clik_skill_launch_info.restype = i32

@@ -97,7 +97,10 @@ clik_status clik_pinv_rollout(const clik_skill* skill, int64_t N, int32_t steps,
                               int32_t* n_failed, void* stream);
 
 /* ReactiveQPController.solve (reactive_qp.py:461-528) for N instances.
- *   x0     [qp_n * N] primal warm start or NULL (as the reference's x0=, :495-513)
+ *   x0     [qp_n * N] primal warm start or NULL (as the reference's x0=, :495-513): used to guess
+ *          the working set (rows that sit on a bound at x0); never changes the answer
+ *   active0 [2 * N] or NULL: explicit working-set guess in the format of `active` (e.g. the
+ *          previous step's output; may alias `active`); takes precedence over x0
  *   sol    [qp_n * N] out: [robot vel; virtual vel; slack]
  *   status [N] out, may be NULL: CLIK_QP_*
  *   active [2 * N] out, may be NULL: active[i] bit r = row r at its upper bound,
@@ -105,8 +108,8 @@ clik_status clik_pinv_rollout(const clik_skill* skill, int64_t N, int32_t steps,
  *   max_iter <= 0 selects the default cap 10 * (qp_n + qp_m). */
 clik_status clik_qp_step(const clik_skill* skill, int64_t N, const double* t, int32_t t_stride,
                          const double* q, const double* x, const double* y, const double* x0,
-                         double* sol, int32_t* status, uint32_t* active, int32_t max_iter,
-                         void* stream);
+                         const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
+                         int32_t max_iter, void* stream);
 
 /* The same simulation loop with the QP controller (see clik_pinv_rollout).  A step whose QP is not
  * solved applies zero velocity and is counted in n_failed (the reference would raise there).
@@ -131,7 +134,8 @@ clik_status clik_pinv_step_host(const clik_skill* skill, int64_t N, const double
                                 const double* y, double* qdot, double* xdot, int32_t* mode);
 clik_status clik_qp_step_host(const clik_skill* skill, int64_t N, const double* t, int32_t t_stride,
                               const double* q, const double* x, const double* y, const double* x0,
-                              double* sol, int32_t* status, uint32_t* active, int32_t max_iter);
+                              const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
+                              int32_t max_iter);
 
 /* Launch geometry chosen at load time (for reporting). */
 clik_status clik_skill_launch_info(const clik_skill* skill, int32_t which /*0 pinv, 1 qp, 2 pinv TMA-staged*/,

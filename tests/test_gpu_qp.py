@@ -78,9 +78,22 @@ def test_ur5_qp_parity_and_kkt():
     sh, sth, ah = ctrl.solve_batch(inp["t"], inp["q"], None, inp["y"])
     assert np.array_equal(sh, sol) and np.array_equal(sth, status)
     assert np.array_equal(ah.astype(np.uint32), active)
-    # warm start (primal guess, as the reference's x0=) does not change the answer
+    # warm starts (primal guess as the reference's x0=, or the previous working set) only shorten
+    # the iteration: same minimiser (to rounding: the iterates differ), same flags
     sw, stw, aw = _solve_device(ctrl, inp, warm=sol)
-    assert np.array_equal(sw, sol) and np.array_equal(aw, active)
+    assert np.all(stw == 0) and np.abs(sw - sol).max() < 1e-11 and np.array_equal(aw, active)
+    torch = _torch()
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    s2, st2, a2 = ctrl.solve_batch(up(inp["t"]), up(inp["q"]), None, up(inp["y"]),
+                                   warm_active=up(active.astype(np.int32)))
+    assert bool((st2 == 0).all()) and np.abs(s2.cpu().numpy() - sol).max() < 1e-11
+    assert np.array_equal(a2.cpu().numpy().astype(np.uint32), active)
+    # a deliberately wrong guess (everything at its upper bound) still gives the right answer
+    bad = np.zeros_like(active, dtype=np.int32)
+    bad[0, :] = 0x7fff
+    s3, st3, a3 = ctrl.solve_batch(up(inp["t"]), up(inp["q"]), None, up(inp["y"]), warm_active=up(bad))
+    assert bool((st3 == 0).all()) and np.abs(s3.cpu().numpy() - sol).max() < 1e-11
+    assert np.array_equal(a3.cpu().numpy().astype(np.uint32), active)
 
 
 def test_moe2016_qp_time_varying_parity():
@@ -196,8 +209,10 @@ def test_qp_rollout_on_device_matches_stepwise_loop():
     q_roll = torch.from_numpy(inp["q"]).cuda()
     q_loop = q_roll.clone()
     out = ctrl.rollout_batch(t0, q_roll, K, dt, max_speed=vmax)
+    act = None
     for k in range(K):
-        sol, status, _ = ctrl.solve_batch(t0 + dt * k, q_loop)
+        # the rollout kernel warm-starts each step from the previous working set: do the same
+        sol, status, act = ctrl.solve_batch(t0 + dt * k, q_loop, warm_active=act)
         assert bool((status == 0).all())
         v = torch.clamp(sol[:6], -vmax, vmax)
         q_loop = q_loop + v * dt

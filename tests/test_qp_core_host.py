@@ -151,12 +151,13 @@ struct S {
   static constexpr double unit_coef(int i) { constexpr double t[7] = {1.0, 1.0, -1.0, 2.0, 1.0, -0.5, 1.0}; return t[i]; }
 };
 extern "C" int host_qps(const double* Ad, const double* lbd, const double* ubd, const double* lbu,
-                        const double* ubu, const double* s, double* x, unsigned* au, unsigned* al, int max_iter) {
+                        const double* ubu, const double* s, double* x, unsigned* au, unsigned* al, int max_iter,
+                        unsigned wu, unsigned wl) {
   clik::QpSData<S> d;
   std::memcpy(d.Ad, Ad, sizeof(d.Ad)); std::memcpy(d.lbd, lbd, sizeof(d.lbd)); std::memcpy(d.ubd, ubd, sizeof(d.ubd));
   std::memcpy(d.lbu, lbu, sizeof(d.lbu)); std::memcpy(d.ubu, ubu, sizeof(d.ubu)); std::memcpy(d.s, s, sizeof(d.s));
   double xs[S::QN];
-  int st = clik::qp_structured<S>(d, xs, au, al, max_iter);
+  int st = clik::qp_structured<S>(d, xs, au, al, max_iter, wu, wl);
   for (int j = 0; j < S::QN; ++j) x[j] = xs[j];
   return st;
 }
@@ -174,7 +175,7 @@ def host_qps(tmp_path_factory):
     subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", str(so), str(src)], check=True)
     lib = ctypes.CDLL(str(so))
 
-    def solve(h, A, lb, ub, max_iter=400):
+    def solve(h, A, lb, ub, max_iter=400, warm=(0, 0)):
         Ad = np.ascontiguousarray(A[DENSE_ROWS])
         ur = [r for r, _, _ in UNIT]
         arrs = [Ad, lb[DENSE_ROWS], ub[DENSE_ROWS], lb[ur], ub[ur], 1.0 / np.sqrt(h)]
@@ -182,7 +183,8 @@ def host_qps(tmp_path_factory):
         x = np.zeros(6)
         au, al = ctypes.c_uint(), ctypes.c_uint()
         st = lib.host_qps(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs],
-                          x.ctypes.data_as(ctypes.c_void_p), ctypes.byref(au), ctypes.byref(al), max_iter)
+                          x.ctypes.data_as(ctypes.c_void_p), ctypes.byref(au), ctypes.byref(al), max_iter,
+                          ctypes.c_uint(warm[0]), ctypes.c_uint(warm[1]))
         return x, st, au.value, al.value
     return solve
 
@@ -241,3 +243,34 @@ def test_structured_solver_infeasible_and_cap(host_qps):
     assert st3 == ok
     _, st1, _, _ = host_qps(h, A, lb3, ub3, 1)
     assert st1 in (1, 2)
+
+
+def test_structured_solver_warm_start_never_changes_the_answer(host_qps):
+    """Working-set guesses: the exact final set, the final set of a perturbed problem (what a
+    rollout hands over), and random garbage.  Same solution and flags as the cold start; a guess
+    that cannot be repaired makes the solver report failure at worst (callers then restart cold),
+    never a wrong 'solved'."""
+    rng = np.random.default_rng(21)
+    n_warm_ok = 0
+    for trial in range(300):
+        h, A, lb, ub = _structured_problem(rng, tight=(trial % 2 == 0))
+        x, st, au, al = host_qps(h, A, lb, ub)
+        assert st == 0
+        guesses = [(au, al)]
+        dl = rng.normal(scale=0.02, size=9)
+        xp, stp, aup, alp = host_qps(h, A + 0.0, lb + dl, ub + dl)
+        if stp == 0:
+            guesses.append((aup, alp))
+        guesses.append((int(rng.integers(0, 512)), 0))
+        up_bits = int(rng.integers(0, 512))
+        guesses.append((up_bits, int(rng.integers(0, 512)) & ~up_bits))
+        for g in guesses:
+            xw, stw, auw, alw = host_qps(h, A, lb, ub, warm=g)
+            if stw != 0:
+                continue                      # unrepaired guess: the kernels retry cold
+            n_warm_ok += 1
+            assert np.abs(xw - x).max() < 1e-9 * (1 + np.abs(x).max()), (trial, g)
+            kk = orc.kkt_residuals(h, A, lb, ub, xw)
+            assert kk["primal"] < 1e-9 and kk["stationarity"] < 1e-9 and kk["sign"] < 1e-9, (trial, g, kk)
+            assert (auw, alw) == (au, al), (trial, g)
+    assert n_warm_ok > 1000
