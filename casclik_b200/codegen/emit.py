@@ -366,6 +366,11 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out.append(_switch("row0", [b["row0"] for b in pinv.blocks]))
         out.append(_switch("rows", [b["rows"] for b in pinv.blocks]))
         out.append(_switch("set_index", [max(b["set_index"], 0) for b in pinv.blocks]))
+        out.append("  static constexpr bool MULTIDIM = %s;   // options[\"multidim_sets\"]" % ("true" if pinv.multidim else "false"))
+        row_is_set = []
+        for b in pinv.blocks:
+            row_is_set += [1 if b["kind"] == KIND_SET else 0] * b["rows"]
+        out.append(_switch("row_is_set", row_is_set, ret="bool"))
         eq_slots, nxt = [], 0
         for b in pinv.blocks:
             if b["kind"] in (KIND_EQ, KIND_VELEQ):
@@ -424,6 +429,8 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
                     em.assign("d.jt[%d]" % gr, b["jt"][r])
                     em.assign("d.smin[%d]" % gr, b["smin"][r])
                     em.assign("d.smax[%d]" % gr, b["smax"][r])
+                    if pinv.multidim:
+                        em.assign("d.rmask[%d]" % gr, b["rmask"][r])
         body = em.finish()
         out.append("  __device__ static __forceinline__ void eval(%s, clik::PinvData<Skill>& d) {" % sig)
         out += ["    " + ln for ln in body]

@@ -76,10 +76,11 @@ class PinvProgram(object):
         state = spec.robot_var if spec.virtual_var is None else cs.vertcat(spec.robot_var,
                                                                          spec.virtual_var)
         ff = bool(options["feedforward"])
-        if options["multidim_sets"] or options["converge_final_set_to_max"]:
+        if options["converge_final_set_to_max"]:
             raise NotImplementedError(
-                "multidim_sets / converge_final_set_to_max (experimental in the reference, "
-                "pseudo_inverse.py:192-257,337-379) are not implemented by the CUDA kernel yet")
+                "converge_final_set_to_max (experimental in the reference, pseudo_inverse.py:337-379) "
+                "is not implemented by the CUDA kernel")
+        self.multidim = bool(options["multidim_sets"])
         method = options["pinv_method"]
         if method not in ("damped", "standard"):
             raise ValueError("pinv_method must be 'damped' or 'standard'")
@@ -93,7 +94,7 @@ class PinvProgram(object):
             if kind == KIND_VELSET:
                 continue  # no branch of the reference's loop matches it (Appendix A6)
             rows = c.expression.size()[0]
-            if kind == KIND_SET and rows > 1:
+            if kind == KIND_SET and rows > 1 and not self.multidim:
                 raise NotImplementedError(
                     "PseudoInverseController does not yet have guaranteed stable support for "
                     "multidimensional SetConstraints. Size(" + c.label + ")=" + str(rows)
@@ -117,6 +118,10 @@ class PinvProgram(object):
             else:
                 blk["smin"] = _col(c.set_min, rows, "set_min", c.label)
                 blk["smax"] = _col(c.set_max, rows, "set_max", c.label)
+                if self.multidim:
+                    # S = diag(e - max > 0 or e - min < 0)              pseudo_inverse.py:289-298
+                    blk["rmask"] = [dag.logic_or(dag.lt(dag.ZERO, dag.sub(en, mx)), dag.lt(dag.sub(en, mn), dag.ZERO))
+                                    for en, mn, mx in zip(blk["e"], blk["smin"], blk["smax"])]
                 blk["set_index"] = set_idx
                 set_idx += 1
             self.blocks.append(blk)
@@ -133,7 +138,7 @@ class PinvProgram(object):
         self.unit_sets = None
         sets = [b for b in self.blocks if b["kind"] == KIND_SET]
         tasks = [b for b in self.blocks if b["kind"] in (KIND_EQ, KIND_VELEQ)]
-        if sets and len(tasks) == 1 and self.blocks[-1] is tasks[0]:
+        if sets and len(tasks) == 1 and self.blocks[-1] is tasks[0] and not self.multidim:
             info, cols = [], set()
             for b in sets:
                 nz = [(j, n) for j, n in enumerate(b["J"][0]) if n is not dag.ZERO]
@@ -146,7 +151,7 @@ class PinvProgram(object):
             self.unit_sets = info
         for b in self.blocks:
             nodes = b["e"] + b["jt"] + [n for r in b["J"] for n in r]
-            nodes += b.get("des", []) + b.get("smin", []) + b.get("smax", [])
+            nodes += b.get("des", []) + b.get("smin", []) + b.get("smax", []) + b.get("rmask", [])
             self.syms.check_closed(nodes, "constraint " + b["label"])
 
 

@@ -32,7 +32,7 @@ class ConicSolver(object):
         dev = torch.device("cuda", runtime.current_device())
 
         def up(a):  # instance-major host array -> coordinate-major device tensor
-            return torch.from_numpy(np.ascontiguousarray(a.reshape(N, -1).T)).to(dev)
+            return torch.from_numpy(np.array(a.reshape(N, -1).T, dtype=np.float64, order="C", copy=True)).to(dev)
         h_d, A_d, lb_d, ub_d = up(hdiag), up(A), up(lb), up(ub)
         x0_d = up(np.asarray(x0, dtype=np.float64)) if x0 is not None else None
         sol = torch.empty((nx, N), dtype=torch.float64, device=dev)

@@ -40,6 +40,7 @@ template <class S> struct PinvData {
   double jt[Max<S::M, 1>::v];          // Set rows: de/dt
   double smin[Max<S::M, 1>::v];        // Set rows: bounds
   double smax[Max<S::M, 1>::v];
+  double rmask[Max<S::M, 1>::v];       // multidim_sets only: 1 if the set row is outside its bounds
 };
 
 // ---- compile-time row lists ------------------------------------------------------------------
@@ -172,8 +173,11 @@ __device__ __forceinline__ void pinv_times(const double (&J)[Max<S::M * S::NS, 1
 }
 
 // x <- (I - P(J_rows) J_rows) x        reference pseudo_inverse.py:387-393 (rJ = J without multidim sets)
+// With options["multidim_sets"] the reduced stack rJ = S J (S = diag(row is outside its bounds),
+// pseudo_inverse.py:289-298, :401-402) replaces J inside the product only: b = rmask .* (J x).
 template <class S, class R>
-__device__ __forceinline__ void nullspace_apply(const double (&J)[Max<S::M * S::NS, 1>::v], double (&x)[S::NS]) {
+__device__ __forceinline__ void nullspace_apply(const double (&J)[Max<S::M * S::NS, 1>::v],
+                                                const double (&rmask)[Max<S::M, 1>::v], double (&x)[S::NS]) {
   constexpr int K = R::size;
   constexpr int NS = S::NS;
   double b[Max<K, 1>::v];
@@ -188,7 +192,11 @@ __device__ __forceinline__ void nullspace_apply(const double (&J)[Max<S::M * S::
         first = false;
       }
     }
-    b[a] = acc;
+    if constexpr (S::MULTIDIM) {
+      b[a] = (S::row_is_set(R::get(a))) ? acc * rmask[R::get(a)] : acc;
+    } else {
+      b[a] = acc;
+    }
   }
   double corr[NS];
   pinv_times<S, R>(J, b, corr);
@@ -336,7 +344,7 @@ template <class S, unsigned MASK, int C, class Stack, bool PRE> struct StaticMod
               }
 #pragma unroll
               for (int j = 0; j < S::NS; ++j) v[j] += w[j];
-              nullspace_apply<S, S1>(d.J, w);
+              nullspace_apply<S, S1>(d.J, d.rmask, w);
 #pragma unroll
               for (int j = 0; j < S::NS; ++j) v[j] += w[j];
             }
@@ -359,7 +367,7 @@ template <class S, unsigned MASK, int C, class Stack, bool PRE> struct StaticMod
           } else {
             pinv_times<S, RC>(d.J, b, w);
           }
-          nullspace_apply<S, Stack>(d.J, w);                              // :387-394 / :434-441
+          nullspace_apply<S, Stack>(d.J, d.rmask, w);                     // :387-394 / :434-441
 #pragma unroll
           for (int j = 0; j < S::NS; ++j) v[j] += w[j];
           StaticMode<S, MASK, C + 1, typename Concat<Stack, RC>::type, PRE>::run(d, tw, v);
@@ -382,29 +390,80 @@ __device__ __forceinline__ bool in_tangent_cone(double e, double de, double smin
   return (smin - e < 1e-12) ? ((e - smax < 1e-12) ? true : (de < 0.0)) : (de > 0.0);
 }
 
+// Vector-valued set (options["multidim_sets"], reference pseudo_inverse.py:222-252): inside <=> every
+// e - min >= 1e-12 and every e - max <= 1e-12; otherwise the motion must point inwards, with a
+// 45-degree rule when every component is outside.  de = de/dt + J v.
+template <int MR>
+__device__ __forceinline__ bool in_tangent_cone_multidim(const double* e, const double* de, const double* smin,
+                                                         const double* smax) {
+  bool above = true, below = true, corner = true;
+  double proj = 0.0, dd = 0.0, oo = 0.0;
+#pragma unroll
+  for (int r = 0; r < MR; ++r) {
+    const double le = e[r] - smin[r], ue = e[r] - smax[r];
+    above = above && (le >= 1e-12);
+    below = below && (ue <= 1e-12);
+    const double sl = (double)((le > 0.0) - (le < 0.0)), su = (double)((ue > 0.0) - (ue < 0.0));
+    corner = corner && (sl == su);
+    const double od = (sl + su) / 2.0;
+    proj += od * de[r];
+    dd += de[r] * de[r];
+    oo += od * od;
+  }
+  if (above && below) return true;
+  if (corner) {
+    if (!(proj < 0.0)) return false;
+    const double dists = (sqrt(dd) + 1e-10) * sqrt(oo);
+    return fabs(-proj) / dists < 0.70710678118654757;   // cos(pi/4)
+  }
+  return proj < 0.0;
+}
+
+// in-tangent-cone test of set constraint C for a candidate velocity v (1 row or vector-valued)
+template <class S, int C>
+__device__ __forceinline__ bool set_admissible(const PinvData<S>& d, const double (&v)[S::NS]) {
+  constexpr int r0 = S::row0(C);
+  constexpr int m = S::rows(C);
+  double de[m];
+#pragma unroll
+  for (int a = 0; a < m; ++a) {
+    double dot = 0.0;
+    bool first = true;
+#pragma unroll
+    for (int j = 0; j < S::NS; ++j) {
+      if (S::jnz(r0 + a, j)) {
+        dot = first ? d.J[(r0 + a) * S::NS + j] * v[j] : fma(d.J[(r0 + a) * S::NS + j], v[j], dot);
+        first = false;
+      }
+    }
+    de[a] = d.jt[r0 + a] + dot;
+  }
+  if constexpr (m == 1) {
+    return in_tangent_cone(d.e[r0], de[0], d.smin[r0], d.smax[r0]);
+  } else {
+    return in_tangent_cone_multidim<m>(&d.e[r0], de, &d.smin[r0], &d.smax[r0]);
+  }
+}
+
+template <class S, unsigned MASK, int C = 0>
+__device__ __forceinline__ bool inactive_sets_admissible(const PinvData<S>& d, const double (&v)[S::NS]) {
+  if constexpr (C < S::NC) {
+    bool ok = true;
+    if constexpr (S::kind(C) == KIND_SET) {
+      if constexpr (!((MASK >> S::set_index(C)) & 1u)) ok = set_admissible<S, C>(d, v);
+    }
+    return ok && inactive_sets_admissible<S, MASK, C + 1>(d, v);
+  } else {
+    return true;
+  }
+}
+
 template <class S, unsigned MASK, bool PRE>
 __device__ __forceinline__ bool static_mode(const PinvData<S>& d, const TaskVel<S>& tw, double (&v)[S::NS]) {
 #pragma unroll
   for (int j = 0; j < S::NS; ++j) v[j] = 0.0;
   StaticMode<S, MASK, 0, Rows<>, PRE>::run(d, tw, v);
-  bool ok = true;
-#pragma unroll
-  for (int c = 0; c < S::NC; ++c) {
-    if (S::kind(c) == KIND_SET && !((MASK >> S::set_index(c)) & 1u)) {
-      const int r = S::row0(c);
-      double dot = 0.0;
-      bool first = true;
-#pragma unroll
-      for (int j = 0; j < S::NS; ++j) {
-        if (S::jnz(r, j)) {
-          dot = first ? d.J[r * S::NS + j] * v[j] : fma(d.J[r * S::NS + j], v[j], dot);
-          first = false;
-        }
-      }
-      ok = ok && in_tangent_cone(d.e[r], d.jt[r] + dot, d.smin[r], d.smax[r]);
-    }
-  }
-  return ok;
+  return inactive_sets_admissible<S, MASK>(d, v);
 }
 
 // ---- one mode, mode mask known only at run time (the rare path) -------------------------------------
@@ -495,23 +554,51 @@ __device__ __noinline__ bool dynamic_mode(const PinvData<S>* d, const TaskVel<S>
         for (int a = 0; a < k; ++a) {
           double acc = 0.0;
           for (int j = 0; j < NS; ++j) acc = fma(d->J[stack[a] * NS + j], w[j], acc);
-          b[a] = acc;
+          b[a] = (S::MULTIDIM && S::row_is_set(stack[a])) ? acc * d->rmask[stack[a]] : acc;
         }
         dyn_pinv_times<S>(d->J, stack, k, b, corr);
         for (int j = 0; j < NS; ++j) v[j] += w[j] - corr[j];
         for (int a = 0; a < m; ++a) stack[k++] = r0 + a;
       }
     } else if (kind == KIND_SET) {
-      if ((mask >> S::set_index(c)) & 1u) stack[k++] = r0;
+      if ((mask >> S::set_index(c)) & 1u) {
+        for (int a = 0; a < m; ++a) stack[k++] = r0 + a;
+      }
     }
   }
   bool ok = true;
   for (int c = 0; c < S::NC; ++c) {
     if (S::kind(c) == KIND_SET && !((mask >> S::set_index(c)) & 1u)) {
-      const int r = S::row0(c);
-      double dot = 0.0;
-      for (int j = 0; j < NS; ++j) dot = fma(d->J[r * NS + j], v[j], dot);
-      ok = ok && in_tangent_cone(d->e[r], d->jt[r] + dot, d->smin[r], d->smax[r]);
+      const int r0 = S::row0(c), m = S::rows(c);
+      double de[S::MAXROWS];
+      for (int a = 0; a < m; ++a) {
+        double dot = 0.0;
+        for (int j = 0; j < NS; ++j) dot = fma(d->J[(r0 + a) * NS + j], v[j], dot);
+        de[a] = d->jt[r0 + a] + dot;
+      }
+      if (m == 1) {
+        ok = ok && in_tangent_cone(d->e[r0], de[0], d->smin[r0], d->smax[r0]);
+      } else {
+        // run-time row count: same rule as in_tangent_cone_multidim
+        bool above = true, below = true, corner = true;
+        double proj = 0.0, dd = 0.0, oo = 0.0;
+        for (int a = 0; a < m; ++a) {
+          const double le = d->e[r0 + a] - d->smin[r0 + a], ue = d->e[r0 + a] - d->smax[r0 + a];
+          above = above && (le >= 1e-12);
+          below = below && (ue <= 1e-12);
+          const double sl = (double)((le > 0.0) - (le < 0.0)), su = (double)((ue > 0.0) - (ue < 0.0));
+          corner = corner && (sl == su);
+          const double od = (sl + su) / 2.0;
+          proj += od * de[a];
+          dd += de[a] * de[a];
+          oo += od * od;
+        }
+        bool in_tc;
+        if (above && below) in_tc = true;
+        else if (corner) in_tc = (proj < 0.0) && (fabs(-proj) / ((sqrt(dd) + 1e-10) * sqrt(oo)) < 0.70710678118654757);
+        else in_tc = proj < 0.0;
+        ok = ok && in_tc;
+      }
     }
   }
   return ok;

@@ -170,6 +170,27 @@ def ur5_moe2016(controller="pinv"):
                     "time-varying 3-row path EqualityConstraint (K=0.15)")
 
 
+def ur5_moe2016_multidim():
+    """The notebook's `skill_multidim` (ur5_moe2016_example2.ipynb cell 8): one 3-row box
+    SetConstraint + path Eq, run with options {"multidim_sets": True} (experimental in the reference)."""
+    t = cs.MX.sym("t")
+    q = cs.MX.sym("q", 6)
+    dq = cs.MX.sym("dq", 6)
+    cx, cy, cz, cp = _moe_constraints(t, q)
+    p = cs.vertcat(cx.expression, cy.expression, cz.expression)
+    box = SetConstraint(label="colav_box", expression=p, set_min=np.array([0.1, -0.5, -0.3]),
+                        set_max=np.array([0.6, 0.4, 0.25]), priority=7, gain=5e2)
+    spec = SkillSpecification(label="box_move_multidim", time_var=t, robot_var=q, robot_vel_var=dq,
+                              constraints=[box, cp])
+
+    def sampler(N, rng):
+        return {"t": rng.uniform(0.0, 80.0, size=N), "q": _ur5_q(N, rng), "x": None, "y": None}
+
+    return Scenario("ur5_moe2016_multidim", spec, "pinv", {"multidim_sets": True}, sampler,
+                    "UR5 (DH FK) Moe-2016 example 2, multidim variant: one 3-row box SetConstraint "
+                    "(2 modes, options multidim_sets=True) + time-varying 3-row path EqualityConstraint")
+
+
 REGISTRY = {
     "ur5_track": ur5_track,
     "iiwa_multitask": iiwa_multitask,
@@ -177,6 +198,7 @@ REGISTRY = {
     "ur5_qp": ur5_qp,
     "ur5_moe2016_pinv": lambda: ur5_moe2016("pinv"),
     "ur5_moe2016_qp": lambda: ur5_moe2016("qp"),
+    "ur5_moe2016_multidim": ur5_moe2016_multidim,
 }
 
 

@@ -154,6 +154,25 @@ def in_tangent_cone(e, de, set_min, set_max):
 # pseudo_inverse.py:259-451 (one mode) and :512-556 (mode search)
 # ----------------------------------------------------------------------------------------------
 
+def in_tangent_cone_multidim(e, de, set_min, set_max):
+    """pseudo_inverse.py:222-252 for a vector-valued set; e, de, bounds are (N, m).
+    inside <=> every e - min >= 1e-12 and every e - max <= 1e-12; otherwise the motion must point
+    inwards, with a 45-degree rule when every component is outside (a "corner")."""
+    le = e - set_min
+    ue = e - set_max
+    le_good = le >= 1e-12
+    ue_good = ue <= 1e-12
+    inside = le_good.all(axis=1) & ue_good.all(axis=1)
+    out_dir = (np.sign(le) + np.sign(ue)) / 2.0
+    corner = (np.sign(le) == np.sign(ue)).all(axis=1)
+    proj = np.einsum("nj,nj->n", out_dir, de)
+    dists = (np.sqrt(np.einsum("nj,nj->n", de, de)) + 1e-10) * np.sqrt(np.einsum("nj,nj->n", out_dir, out_dir))
+    with np.errstate(all="ignore"):
+        corner_handler = np.where(proj < 0.0, np.abs(-proj) / dists < math.cos(math.pi / 4), False)
+    going_in = np.where(corner, corner_handler, proj < 0.0)
+    return np.where(inside, True, going_in)
+
+
 def _mode_velocity(blocks: Sequence[Block], active_bits: Sequence[int], n: int, N: int, opts):
     """Velocity of one mode for all N instances + the list of inactive scalar sets to test."""
     ff = opts.get("feedforward", True)
@@ -161,8 +180,8 @@ def _mode_velocity(blocks: Sequence[Block], active_bits: Sequence[int], n: int, 
     lam = opts.get("damping_factor", 1e-7)
     conv_last = opts.get("converge_final_set_to_max", False)
     multidim = opts.get("multidim_sets", False)
-    if conv_last or multidim:
-        raise NotImplementedError("oracle covers the default (non-experimental) options")
+    if conv_last:
+        raise NotImplementedError("oracle does not cover converge_final_set_to_max")
     dt = blocks[0].J.dtype
     v = np.zeros((N, n), dtype=dt)
     Jlist, rJlist, to_test = [], [], []
@@ -178,7 +197,7 @@ def _mode_velocity(blocks: Sequence[Block], active_bits: Sequence[int], n: int, 
 
     for b in blocks:
         is_first = len(Jlist) == 0                                     # :276
-        if b.kind == SET and b.rows > 1:
+        if b.kind == SET and b.rows > 1 and not multidim:
             raise NotImplementedError("multi-row SetConstraint needs multidim_sets (:299-312)")
         if b.kind == EQ:
             des = -_gain_times(b.gain, b.e)                            # :318 / :383
@@ -206,8 +225,14 @@ def _mode_velocity(blocks: Sequence[Block], active_bits: Sequence[int], n: int, 
         elif b.kind == SET:
             if active_bits[set_idx]:                                   # :399-405
                 Jlist.append(b.J)
-                rJlist.append(b.J)
-            else:                                                      # :406-410
+                if multidim:                                           # :289-298, :401-402
+                    hi = _bcast(b.set_max, N, b.rows)
+                    lo = _bcast(b.set_min, N, b.rows)
+                    act = ((b.e - hi > 0.0) | (b.e - lo < 0.0)).astype(b.J.dtype)
+                    rJlist.append(act[:, :, None] * b.J)               # S @ Ji, S = diag(active)
+                else:
+                    rJlist.append(b.J)
+            else:                                                      # :406-415
                 to_test.append(b)
             set_idx += 1
         # VELSET: no branch matches -> ignored (Appendix A6)
@@ -241,10 +266,16 @@ def pinv_step(blocks: Sequence[Block], n_state: int, options: Optional[dict] = N
         v, to_test = _mode_velocity(sub, bits, n_state, len(idx), opts)
         ok = np.ones((len(idx),), dtype=bool)
         for b in to_test:
-            de = b.Jt[:, 0] + np.einsum("nj,nj->n", b.J[:, 0, :], v)  # :151-158
-            lo = _bcast(b.set_min, len(idx), 1)[:, 0]
-            hi = _bcast(b.set_max, len(idx), 1)[:, 0]
-            ok &= in_tangent_cone(b.e[:, 0], de, lo, hi).astype(bool)
+            if b.rows == 1:
+                de = b.Jt[:, 0] + np.einsum("nj,nj->n", b.J[:, 0, :], v)  # :151-158
+                lo = _bcast(b.set_min, len(idx), 1)[:, 0]
+                hi = _bcast(b.set_max, len(idx), 1)[:, 0]
+                ok &= in_tangent_cone(b.e[:, 0], de, lo, hi).astype(bool)
+            else:                                                      # :211-218, multidim_sets
+                de = b.Jt + np.einsum("nij,nj->ni", b.J, v)
+                lo = _bcast(b.set_min, len(idx), b.rows)
+                hi = _bcast(b.set_max, len(idx), b.rows)
+                ok &= in_tangent_cone_multidim(b.e, de, lo, hi).astype(bool)
         acc = idx[ok]
         v_out[acc] = v[ok]
         mode_out[acc] = mode_idx

@@ -129,6 +129,9 @@ def test_pinv_controller_attributes_and_mode_table():
     multi = cc.SkillSpecification("m", t, q, constraints=[cc.SetConstraint("box", q), eq])
     with pytest.raises(NotImplementedError):
         cc.PseudoInverseController(multi).setup_problem_functions(load=False)
+    cc.PseudoInverseController(multi, options={"multidim_sets": True}).setup_problem_functions(load=False)
+    with pytest.raises(NotImplementedError):
+        cc.PseudoInverseController(multi, options={"converge_final_set_to_max": True}).setup_problem_functions(load=False)
 
 
 def test_qp_controller_weights_and_options():

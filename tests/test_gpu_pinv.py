@@ -133,6 +133,29 @@ def test_rank_deficient_stress_skill_is_as_accurate_as_the_fp64_reference_formul
     assert e_o64.max() > 1e-9
 
 
+def test_multidim_sets_option_parity():
+    """options["multidim_sets"] (experimental in the reference, pseudo_inverse.py:192-257, :289-298):
+    vector-valued SetConstraint, row-masked reduced Jacobian, vector in-tangent-cone test."""
+    sc, ctrl = _setup("ur5_moe2016_multidim")
+    assert ctrl.n_modes == 2
+    inp = sc.sample(4096, seed=6)
+    ref_v, ref_mode = oracle_pinv(sc.spec, inp, {"multidim_sets": True})
+    v, _, mode = _run_device(ctrl, inp)
+    assert set(np.unique(ref_mode)) >= {0, 1}
+    assert np.array_equal(mode, ref_mode), "mode flags differ in %d instances" % int((mode != ref_mode).sum())
+    assert close(v, ref_v, RTOL, ATOL).all(), _report(v, ref_v, "multidim")
+    # scalar sets under multidim_sets also use the masked reduced Jacobian
+    sc2 = scenarios.get("ur5_moe2016_pinv")
+    c2 = cc.PseudoInverseController(sc2.spec, options={"multidim_sets": True})
+    c2.setup_solver()
+    inp2 = sc2.sample(2048, seed=8)
+    ref2, mode2 = oracle_pinv(sc2.spec, inp2, {"multidim_sets": True})
+    v2, _, m2 = _run_device(c2, inp2)
+    assert np.array_equal(m2, mode2) and close(v2, ref2, RTOL, ATOL).all(), _report(v2, ref2, "scalar sets, multidim")
+    ref_plain, _ = oracle_pinv(sc2.spec, inp2)
+    assert np.abs(ref2 - ref_plain).max() > 1e-6          # the option does change the answer
+
+
 def test_no_admissible_mode_returns_zero_and_minus_one():
     # p must stay in [0, 1] but the only task pushes it further out and the set itself cannot
     # produce motion (A5): with p = 2 and target 3 every mode is rejected or ...
