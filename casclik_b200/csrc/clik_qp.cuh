@@ -642,6 +642,12 @@ __device__ __forceinline__ void qp_step(long long N, const double* __restrict__ 
 #pragma unroll
         for (int j = 0; j < S::QN; ++j) x0v[j] = x0[(long long)j * N + i];
         masks_from_x0<S>(d, x0v, &wu, &wl);
+      } else if (S::QP_EQ_START) {
+        // no guess: equality rows are active at every solution, start with them held
+#pragma unroll
+        for (int a = 0; a < S::QMD; ++a) {
+          if (S::dense_row(a) < 32 && d.lbd[a] == d.ubd[a]) wu |= 1u << S::dense_row(a);
+        }
       }
       st = QP_MAXITER;
 #pragma unroll 1
