@@ -211,6 +211,18 @@ class GenericMatrixCommon(object):
             body = "..."
         return "%s(%dx%d %s)" % (type(self).__name__, r, c, body)
 
+    def __str__(self):
+        """Constant matrices print like CasADi's DM ("1.0192", "[1, 2, 3]", "[[1, 0], \n [0, 1]]")."""
+        if not self.is_constant() or self._a.size == 0:
+            return repr(self)
+        fmt = lambda n: "%g" % n.val  # noqa: E731
+        r, c = self._a.shape
+        if (r, c) == (1, 1):
+            return fmt(self._a[0, 0])
+        if c == 1:
+            return "[" + ", ".join(fmt(n) for n in self._a[:, 0]) + "]"
+        return "[" + ", \n ".join("[" + ", ".join(fmt(n) for n in row) + "]" for row in self._a) + "]"
+
     # ---- indexing ----------------------------------------------------------------------------
     def _norm_index(self, key):
         r, c = self._a.shape

@@ -132,3 +132,10 @@ def test_small_linear_algebra():
     assert np.allclose(P, np.linalg.pinv(np.hstack([Mn, [[0.3], [-0.7]]])))
     assert np.allclose(cs.cross([1., 0, 0], [0, 1., 0]).toarray()[:, 0], [0, 0, 1])
     assert abs(float(cs.norm_fro(np.eye(3))) - np.sqrt(3)) < 1e-15
+
+
+def test_dm_prints_like_casadi():
+    assert str(cs.DM(1.0192017582309205)) == "1.0192"
+    assert str(cs.DM([1, 2, 3])) == "[1, 2, 3]"
+    assert "Distance: " + str(cs.norm_2(cs.DM([3.0, 4.0]))) == "Distance: 5"
+    assert str(cs.MX.sym("q", 2)).startswith("MX(2x1")
