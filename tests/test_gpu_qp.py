@@ -219,3 +219,37 @@ def test_qp_rollout_on_device_matches_stepwise_loop():
     torch.cuda.synchronize()
     assert torch.equal(q_roll, q_loop)
     assert torch.equal(out["sol"][:6], v) and int(out["n_failed"].sum()) == 0
+
+
+def test_kitchen_sink_qp_parity():
+    """Expression-valued weights and bounds, matrix gains, hard + soft rows of every constraint
+    class, virtual and input variables — through the generic (many dense rows) solver."""
+    t, q, dq = cs.MX.sym("t"), cs.MX.sym("q", 3), cs.MX.sym("dq", 3)
+    x, dx, y = cs.MX.sym("x"), cs.MX.sym("dx"), cs.MX.sym("y", 2)
+    c1 = cc.EqualityConstraint("soft_eq", cs.vertcat(cs.sin(q[0]) + q[1] - y[0], q[2] * q[0] - y[1] + 0.1 * x),
+                               gain=np.array([[2.0, 0.3], [0.0, 1.5]]), constraint_type="soft", slack_weight=3.0)
+    c2 = cc.SetConstraint("soft_set", q[1] + 0.2 * cs.sin(t), gain=3.0, set_min=-0.4, set_max=cs.MX(0.5) + 0.05 * y[1],
+                          constraint_type="soft")
+    c3 = cc.VelocityEqualityConstraint("hard_veleq", q[0] + 0.5 * q[2] + x, target=0.2 * cs.sin(t))
+    c4 = cc.VelocitySetConstraint("speed", q, set_min=-0.8 * np.ones(3), set_max=0.8 * np.ones(3))
+    c5 = cc.VelocitySetConstraint("vspeed", x, set_min=-0.5, set_max=0.5)
+    spec = cc.SkillSpecification("qp_sink", t, q, robot_vel_var=dq, virtual_var=x, virtual_vel_var=dx,
+                                 input_var=y, constraints=[c1, c2, c3, c4, c5])
+    ctrl = cc.ReactiveQPController(spec, robot_var_weights=[1.0, 2.0, 0.5], virtual_var_weights=[4.0])
+    ctrl.setup_problem_functions()
+    ctrl.setup_solver()
+    rng = np.random.default_rng(3)
+    N = 1500
+    inp = {"t": rng.uniform(0, 10, N), "q": rng.uniform(-0.6, 0.6, (3, N)), "x": rng.uniform(-1, 1, (1, N)),
+           "y": rng.uniform(-0.5, 0.5, (2, N))}
+    h, A, lb, ub = oracle_qp_problem(spec, inp, w_rob=[1.0, 2.0, 0.5], w_virt=[4.0])
+    assert np.allclose(h, [0.001, 0.002, 0.0005, 0.004, 3.001, 3.001, 1.001])
+    sol, status, active = _solve_device(ctrl, inp)
+    assert np.all(status == 0)
+    for i in range(0, N, 7):
+        xo, lamo, sto = orc.solve_qp_single(h, A[i], lb[i], ub[i])
+        assert sto == 0 and np.abs(sol[:, i] - xo).max() < 1e-7 * (1 + np.abs(xo).max())
+        kk = orc.kkt_residuals(h, A[i], lb[i], ub[i], sol[:, i])
+        assert kk["primal"] < 1e-8 and kk["stationarity"] < 1e-8 and kk["sign"] < 1e-8
+        up_o, lo_o = _masks(lamo[None, :])
+        assert active[0, i] == up_o[0] and active[1, i] == lo_o[0]
