@@ -216,42 +216,48 @@ __device__ __forceinline__ int qp_structured(QpSData<S>& D, double (&x)[S::QN], 
 #pragma unroll
   for (int i = 0; i < MU; ++i) ks[i] = S::unit_coef(i) * D.s[S::unit_col(i)];
 
-  // QR of the active dense normals on the free coordinates, rebuilt in slot order
+  // QR of the active dense normals on the free coordinates, rebuilt in slot order.  Branch-free:
+  // an inactive slot has a zero column (Qd row = 0, iRd = 0, its Rd entries = 0), so every loop
+  // of the iteration can run over all MD slots without per-thread control flow.
   auto refactor = [&]() {
 #pragma unroll
     for (int a = 0; a < MD; ++a) {
-      if (ad[a] != 0) {
-        double col[NX];
+      const double sa = (double)ad[a];
+      double col[NX];
 #pragma unroll
-        for (int j = 0; j < NX; ++j) col[j] = (nF[j] != 0.0) ? 0.0 : (double)ad[a] * D.Ad[a * NX + j];
+      for (int j = 0; j < NX; ++j) col[j] = (nF[j] != 0.0) ? 0.0 : sa * D.Ad[a * NX + j];
 #pragma unroll
-        for (int l = 0; l < a; ++l) Rd[l * MD1 + a] = 0.0;
+      for (int l = 0; l < a; ++l) Rd[l * MD1 + a] = 0.0;
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
+      for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-          for (int l = 0; l < a; ++l) {
-            if (ad[l] != 0) {
-              double dt = 0.0;
+        for (int l = 0; l < a; ++l) {
+          double dt = 0.0;
 #pragma unroll
-              for (int j = 0; j < NX; ++j) dt = fma(Qd[l * NX + j], col[j], dt);
+          for (int j = 0; j < NX; ++j) dt = fma(Qd[l * NX + j], col[j], dt);
 #pragma unroll
-              for (int j = 0; j < NX; ++j) col[j] = fma(-dt, Qd[l * NX + j], col[j]);
-              Rd[l * MD1 + a] += dt;
-            }
-          }
+          for (int j = 0; j < NX; ++j) col[j] = fma(-dt, Qd[l * NX + j], col[j]);
+          Rd[l * MD1 + a] += dt;
         }
-        double nrm = 0.0;
-#pragma unroll
-        for (int j = 0; j < NX; ++j) nrm = fma(col[j], col[j], nrm);
-        nrm = sqrt(nrm);
-        Rd[a * MD1 + a] = nrm;
-        const double inv = 1.0 / nrm;
-        iRd[a] = inv;
-#pragma unroll
-        for (int j = 0; j < NX; ++j) Qd[a * NX + j] = col[j] * inv;
       }
+      double nrm = 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) nrm = fma(col[j], col[j], nrm);
+      nrm = sqrt(nrm);
+      Rd[a * MD1 + a] = nrm;
+      const double inv = (ad[a] != 0) ? 1.0 / nrm : 0.0;
+      iRd[a] = inv;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) Qd[a * NX + j] = (ad[a] != 0) ? col[j] * inv : 0.0;
     }
   };
+#pragma unroll
+  for (int a = 0; a < MD; ++a) {
+#pragma unroll
+    for (int j = 0; j < NX; ++j) Qd[a * NX + j] = 0.0;
+#pragma unroll
+    for (int l = 0; l < MD; ++l) Rd[a * MD1 + l] = 0.0;
+  }
 
   if ((warm_up | warm_lo) != 0u) {
     // ---- adopt the guessed working set ---------------------------------------------------------
@@ -374,28 +380,26 @@ __device__ __forceinline__ int qp_structured(QpSData<S>& D, double (&x)[S::QN], 
   for (int it = 0; it < max_iter; ++it) {
     // ---- most violated one-sided constraint (same rule and tolerances as the dense solver) ----
     int p = -1;            // 0..MD-1: dense slot, MD..MD+MU-1: unit row
-    double sp = 0.0, vbest = 0.0;
+    double sp = 0.0, vbest = 0.0, bp = 0.0;   // bp: the violated bound, in the form n_p . z <= bp
 #pragma unroll
     for (int a = 0; a < MD; ++a) {
-      if (ad[a] == 0) {
-        double r = 0.0;
+      double r = 0.0;
 #pragma unroll
-        for (int j = 0; j < NX; ++j) r = fma(D.Ad[a * NX + j], z[j], r);
-        const double vu = r - D.ubd[a], vl = D.lbd[a] - r;
-        const double tu = 1e-12 * fmax(1.0, fabs(D.ubd[a])), tl = 1e-12 * fmax(1.0, fabs(D.lbd[a]));
-        if (vu > tu && vu > vbest) { vbest = vu; p = a; sp = 1.0; }
-        if (vl > tl && vl > vbest) { vbest = vl; p = a; sp = -1.0; }
-      }
+      for (int j = 0; j < NX; ++j) r = fma(D.Ad[a * NX + j], z[j], r);
+      const double vu = r - D.ubd[a], vl = D.lbd[a] - r;
+      const double tu = 1e-12 * fmax(1.0, fabs(D.ubd[a])), tl = 1e-12 * fmax(1.0, fabs(D.lbd[a]));
+      const bool free_ = ad[a] == 0;
+      if (free_ && vu > tu && vu > vbest) { vbest = vu; p = a; sp = 1.0; bp = D.ubd[a]; }
+      if (free_ && vl > tl && vl > vbest) { vbest = vl; p = a; sp = -1.0; bp = -D.lbd[a]; }
     }
 #pragma unroll
     for (int i = 0; i < MU; ++i) {
-      if (frow[S::unit_col(i)] != i) {
-        const double r = ks[i] * z[S::unit_col(i)];
-        const double vu = r - D.ubu[i], vl = D.lbu[i] - r;
-        const double tu = 1e-12 * fmax(1.0, fabs(D.ubu[i])), tl = 1e-12 * fmax(1.0, fabs(D.lbu[i]));
-        if (vu > tu && vu > vbest) { vbest = vu; p = MD + i; sp = 1.0; }
-        if (vl > tl && vl > vbest) { vbest = vl; p = MD + i; sp = -1.0; }
-      }
+      const double r = ks[i] * z[S::unit_col(i)];
+      const double vu = r - D.ubu[i], vl = D.lbu[i] - r;
+      const double tu = 1e-12 * fmax(1.0, fabs(D.ubu[i])), tl = 1e-12 * fmax(1.0, fabs(D.lbu[i]));
+      const bool free_ = frow[S::unit_col(i)] != i;
+      if (free_ && vu > tu && vu > vbest) { vbest = vu; p = MD + i; sp = 1.0; bp = D.ubu[i]; }
+      if (free_ && vl > tl && vl > vbest) { vbest = vl; p = MD + i; sp = -1.0; bp = -D.lbu[i]; }
     }
     if (p < 0) { status = QP_OK; break; }
 
@@ -405,18 +409,18 @@ __device__ __forceinline__ int qp_structured(QpSData<S>& D, double (&x)[S::QN], 
     for (int j = 0; j < NX; ++j) np_[j] = 0.0;
 #pragma unroll
     for (int a = 0; a < MD; ++a) {
-      if (p == a) {
 #pragma unroll
-        for (int j = 0; j < NX; ++j) np_[j] = sp * D.Ad[a * NX + j];
-      }
+      for (int j = 0; j < NX; ++j) np_[j] = (p == a) ? sp * D.Ad[a * NX + j] : np_[j];
     }
 #pragma unroll
     for (int i = 0; i < MU; ++i) {
-      if (p == MD + i) np_[S::unit_col(i)] = sp * ks[i];
+      np_[S::unit_col(i)] = (p == MD + i) ? sp * ks[i] : np_[S::unit_col(i)];
     }
-    double nn = 0.0;
+    double nn = 0.0, vnp = 1.0;
 #pragma unroll
     for (int j = 0; j < NX; ++j) nn = fma(np_[j], np_[j], nn);
+#pragma unroll
+    for (int i = 0; i < MU; ++i) vnp = (p == MD + i) ? sp * ks[i] : vnp;
 
     double up = 0.0;
     bool done = false, infeasible = false;
@@ -430,34 +434,28 @@ __device__ __forceinline__ int qp_structured(QpSData<S>& D, double (&x)[S::QN], 
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-        for (int a = 0; a < MD; ++a) {
-          if (ad[a] != 0) {
-            double dt = 0.0;
+        for (int a = 0; a < MD; ++a) {           // inactive slots have Qd = 0: no-ops
+          double dt = 0.0;
 #pragma unroll
-            for (int j = 0; j < NX; ++j) dt = fma(Qd[a * NX + j], d[j], dt);
+          for (int j = 0; j < NX; ++j) dt = fma(Qd[a * NX + j], d[j], dt);
 #pragma unroll
-            for (int j = 0; j < NX; ++j) d[j] = fma(-dt, Qd[a * NX + j], d[j]);
-            cd[a] += dt;
-          }
+          for (int j = 0; j < NX; ++j) d[j] = fma(-dt, Qd[a * NX + j], d[j]);
+          cd[a] += dt;
         }
       }
 #pragma unroll
       for (int a = MD - 1; a >= 0; --a) {
         double acc = cd[a];
 #pragma unroll
-        for (int l = a + 1; l < MD; ++l) {
-          if (ad[l] != 0) acc = fma(-Rd[a * MD1 + l], rd[l], acc);
-        }
-        rd[a] = (ad[a] != 0) ? acc * iRd[a] : 0.0;
+        for (int l = a + 1; l < MD; ++l) acc = fma(-Rd[a * MD1 + l], rd[l], acc);
+        rd[a] = acc * iRd[a];                      // iRd = 0 for an inactive slot
       }
 #pragma unroll
       for (int j = 0; j < NX; ++j) {
         double acc = np_[j];
 #pragma unroll
-        for (int a = 0; a < MD; ++a) {
-          if (ad[a] != 0) acc = fma(-(double)ad[a] * D.Ad[a * NX + j], rd[a], acc);
-        }
-        rF[j] = (nF[j] != 0.0) ? acc * inF[j] : 0.0;
+        for (int a = 0; a < MD; ++a) acc = fma(-(double)ad[a] * D.Ad[a * NX + j], rd[a], acc);
+        rF[j] = acc * inF[j];                      // inF = 0 for a free coordinate
       }
       double dn = 0.0;
 #pragma unroll
@@ -484,23 +482,9 @@ __device__ __forceinline__ int qp_structured(QpSData<S>& D, double (&x)[S::QN], 
         }
       }
       const double t1 = (drop >= 0) ? ub_ / rb_ : INFINITY;
-      double viol = 0.0;
+      double viol = -bp;                           // n_p . z - bound (> 0: violated)
 #pragma unroll
-      for (int a = 0; a < MD; ++a) {
-        if (p == a) {
-          double r = 0.0;
-#pragma unroll
-          for (int j = 0; j < NX; ++j) r = fma(D.Ad[a * NX + j], z[j], r);
-          viol = (sp > 0.0) ? (r - D.ubd[a]) : (D.lbd[a] - r);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < MU; ++i) {
-        if (p == MD + i) {
-          const double r = ks[i] * z[S::unit_col(i)];
-          viol = (sp > 0.0) ? (r - D.ubu[i]) : (D.lbu[i] - r);
-        }
-      }
+      for (int j = 0; j < NX; ++j) viol = fma(np_[j], z[j], viol);
       const bool independent = (nact < NX) && (dn > 1e-24 * nn);
       const double t2 = independent ? viol / dn : INFINITY;
       const double t = fmin(t1, t2);
@@ -518,17 +502,18 @@ __device__ __forceinline__ int qp_structured(QpSData<S>& D, double (&x)[S::QN], 
         // full step: p joins the working set
 #pragma unroll
         for (int a = 0; a < MD; ++a) {
-          if (p == a) { ad[a] = (sp > 0.0) ? 1 : -1; uD[a] = up; }
+          ad[a] = (p == a) ? ((sp > 0.0) ? 1 : -1) : ad[a];
+          uD[a] = (p == a) ? up : uD[a];
         }
+        const double inv_np = 1.0 / vnp;           // vnp: the single non-zero entry of a unit normal
 #pragma unroll
         for (int i = 0; i < MU; ++i) {
-          if (p == MD + i) {
-            nF[S::unit_col(i)] = sp * ks[i];
-            inF[S::unit_col(i)] = 1.0 / (sp * ks[i]);
-            uF[S::unit_col(i)] = up;
-            frow[S::unit_col(i)] = i;
-            fside[S::unit_col(i)] = (sp > 0.0) ? 1 : -1;
-          }
+          const bool hit = p == MD + i;
+          nF[S::unit_col(i)] = hit ? vnp : nF[S::unit_col(i)];
+          inF[S::unit_col(i)] = hit ? inv_np : inF[S::unit_col(i)];
+          uF[S::unit_col(i)] = hit ? up : uF[S::unit_col(i)];
+          frow[S::unit_col(i)] = hit ? i : frow[S::unit_col(i)];
+          fside[S::unit_col(i)] = hit ? ((sp > 0.0) ? 1 : -1) : fside[S::unit_col(i)];
         }
         ++nact;
         done = true;
@@ -536,11 +521,17 @@ __device__ __forceinline__ int qp_structured(QpSData<S>& D, double (&x)[S::QN], 
         // partial step: release the blocking constraint, try again with the same p
 #pragma unroll
         for (int j = 0; j < NX; ++j) {
-          if (drop == j) { nF[j] = 0.0; inF[j] = 0.0; uF[j] = 0.0; frow[j] = -1; fside[j] = 0; }
+          const bool hit = drop == j;
+          nF[j] = hit ? 0.0 : nF[j];
+          inF[j] = hit ? 0.0 : inF[j];
+          uF[j] = hit ? 0.0 : uF[j];
+          frow[j] = hit ? -1 : frow[j];
+          fside[j] = hit ? 0 : fside[j];
         }
 #pragma unroll
         for (int a = 0; a < MD; ++a) {
-          if (drop == NX + a) { ad[a] = 0; uD[a] = 0.0; }
+          ad[a] = (drop == NX + a) ? 0 : ad[a];
+          uD[a] = (drop == NX + a) ? 0.0 : uD[a];
         }
         --nact;
       }
