@@ -163,6 +163,9 @@ class ReactiveQPController(BaseController):
         self.kernel_source, self.kernel_meta, self.cubin_path = source, meta, path
         self._nxv, self._ny, self._qn, self._qm = prog.n_virt, prog.n_in, prog.nx, prog.m
         self.row_labels = prog.labels
+        # constant cost weights (the usual case): keep the numbers, so `solve` does not have to
+        # evaluate H_func through the expression interpreter at every call
+        self._h_const = (np.array([n.val for n in prog.h]) if all(n.is_const for n in prog.h) else None)
         self._cubin = cubin
         self._compiled = None
         ins, names = self._input_list()
@@ -311,10 +314,11 @@ class ReactiveQPController(BaseController):
             raise RuntimeError("QP %s" % ("is infeasible" if int(status[0]) == runtime.QP_INFEASIBLE
                                           else "hit the iteration cap"))
         xs = sol[:, 0]
+        hdiag = self._h_const if self._h_const is not None else np.asarray(
+            self.H_func(*self._numeric_args(time_var, q, x, y)).toarray()).diagonal()
         self.res = {"x": dm_column(xs), "status": int(status[0]),
                     "active_upper": int(active[0, 0]), "active_lower": int(active[1, 0]),
-                    "cost": 0.5 * float(np.sum(np.asarray(self.H_func(*self._numeric_args(
-                        time_var, q, x, y)).toarray()).diagonal() * xs * xs))}
+                    "cost": 0.5 * float(np.sum(hdiag * xs * xs))}
         res_robot_vel = dm_column(xs[:nrob])
         res_virtual_vel = dm_column(xs[nrob:nrob + nvirt]) if (nvirt > 0 and has_virtual) else None
         off = nrob + self._nxv
