@@ -396,6 +396,12 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         pre_struct.append("__device__ const unsigned short clik_mode_tab[%d] = {%s};" % (
             len(masks), ", ".join(str(v) for v in masks)))
         out.append("  __device__ static __forceinline__ unsigned mode_mask(int mi) { return clik_mode_tab[mi]; }")
+        inv = [0] * len(masks)
+        for mi, mk in enumerate(masks):
+            inv[mk] = mi
+        pre_struct.append("__device__ const unsigned short clik_mode_inv[%d] = {%s};   // mask -> mode index" % (
+            len(masks), ", ".join(str(v) for v in inv)))
+        out.append("  __device__ static __forceinline__ unsigned mode_index(unsigned mask) { return clik_mode_inv[mask]; }")
         # modes compiled on the static register path: all of them when there are at most 8,
         # otherwise those with at most two active sets if that is at most 64 modes (iiwa: 29 of
         # 128, which covers 99.6 % of the random instances of configs[2]), else mode 0 + singles

@@ -680,17 +680,26 @@ __device__ __forceinline__ int solve_instance(const double tv, const double (&qv
     if (static_mode<S, 0u, PRE>(d, tw, v)) return 0;
     int accepted = -1;
     if constexpr (S::UNIT_SETS) {
-      // closed-form modes in registers: no static instantiations, no local-memory path
-      for (int mi = 1; mi < S::NMODES; ++mi) {
-        if (unit_set_mode<S>(d, tw, S::mode_mask(mi), v)) {
-          accepted = mi;
-          break;
+      // Unit sets + task last: for any mode with at least one active set the task is not "first",
+      // v = N(S_M) w, and N only rescales the ACTIVE coordinates.  So whether an inactive set k
+      // passes its in-tangent-cone test depends on w alone, not on the rest of the mode:
+      // mode M is admissible <=> M contains F = {k : set k fails the test under w}.  The
+      // activation map is ordered by number of active sets, so the first admissible non-empty
+      // mode of the reference's sequential search (pseudo_inverse.py:530-550) is F itself
+      // (or the first single-set mode if F is empty: mode 0 failed under its own, doubled,
+      // velocity but every set passes under w).  No search loop.
+      unsigned F = 0u;
+#pragma unroll
+      for (int c = 0; c < S::NC; ++c) {
+        if (S::kind(c) == KIND_SET) {
+          const int k = S::set_index(c);
+          const int r = S::row0(c);
+          const double de = d.jt[r] + S::set_unit_coef(k) * tw.w[0][S::set_unit_col(k)];
+          if (!in_tangent_cone(d.e[r], de, d.smin[r], d.smax[r])) F |= 1u << k;
         }
       }
-      if (accepted < 0) {
-#pragma unroll
-        for (int j = 0; j < S::NS; ++j) v[j] = 0.0;
-      }
+      accepted = (F == 0u) ? 1 : (int)S::mode_index(F);
+      unit_set_mode<S>(d, tw, S::mode_mask(accepted), v);
       return accepted;
     }
     for (int mi = 1; mi < S::NSTATIC; ++mi) {
