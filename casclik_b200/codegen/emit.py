@@ -575,8 +575,14 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out.append("                          max_iter);")
         out.append("}")
     out.append('extern "C" __global__ void clik_sizes_kernel(int* o) {')
-    out.append("  o[0] = %d; o[1] = %d; o[2] = %d; o[3] = %d; o[4] = %d; o[5] = %d; o[6] = %d; o[7] = 0;"
-               % (nq, nxv, ny, meta["n_modes"], meta["qp_n"], meta["qp_m"], meta.get("pinv_unroll", 1)))
+    flags = 0
+    if pinv is not None:
+        flags |= 2 | (1 if os.environ.get("CLIK_TMA", "0") == "1" else 0)
+    if qp is not None:
+        flags |= 4
+    out.append("  // manifest: sizes, unroll, optional-kernel flags (1 pinv TMA, 2 pinv rollout, 4 QP rollout)")
+    out.append("  o[0] = %d; o[1] = %d; o[2] = %d; o[3] = %d; o[4] = %d; o[5] = %d; o[6] = %d; o[7] = %d;"
+               % (nq, nxv, ny, meta["n_modes"], meta["qp_n"], meta["qp_m"], meta.get("pinv_unroll", 1), flags))
     full = (1, 0xffffffff, 0xffffffff, 0xffffffff)
     pm, qm = meta.get("pinv_read_masks", full), meta.get("qp_read_masks", full)
     out.append("  // input rows the kernels read (t, q, x, y bit masks): pinv then QP")

@@ -306,57 +306,48 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
     delete s;
     return fail(CLIK_ERR_IMAGE, "cannot load cubin (%zu bytes): %s", len, cudaGetErrorString(e));
   }
+  // The image carries its own manifest (clik_sizes_kernel): sizes, which optional kernels it
+  // holds, and which input rows its kernels read.  Refuse a descriptor that disagrees.
   clik_status st = CLIK_OK;
-  if (desc->has_pinv) st = setup_kernel(s, "clik_pinv_kernel", &s->pinv);
+  int hsz[16] = {0};
+  {
+    cudaKernel_t probe;
+    cudaError_t pe = cudaLibraryGetKernel(&probe, s->lib, "clik_sizes_kernel");
+    if (pe != cudaSuccess) {
+      st = fail(CLIK_ERR_IMAGE, "cubin has no clik_sizes_kernel manifest: %s", cudaGetErrorString(pe));
+    } else {
+      int* dsz = nullptr;
+      cudaError_t le = cudaMalloc(&dsz, sizeof(hsz));
+      if (le == cudaSuccess) {
+        void* args[] = {&dsz};
+        le = cudaLaunchKernel((const void*)probe, dim3(1), dim3(1), args, 0, nullptr);
+        if (le == cudaSuccess) le = cudaMemcpy(hsz, dsz, sizeof(hsz), cudaMemcpyDeviceToHost);
+        cudaFree(dsz);
+      }
+      if (le != cudaSuccess) {
+        st = fail(CLIK_ERR_CUDA, "size probe failed: %s", cudaGetErrorString(le));
+      } else if (hsz[0] != desc->n_robot || hsz[1] != desc->n_virtual || hsz[2] != desc->n_input ||
+                 hsz[3] != desc->n_modes || hsz[4] != desc->qp_n || hsz[5] != desc->qp_m) {
+        st = fail(CLIK_ERR_IMAGE,
+                  "descriptor does not match cubin: image (n_robot %d, n_virtual %d, n_input %d, "
+                  "n_modes %d, qp %dx%d)",
+                  hsz[0], hsz[1], hsz[2], hsz[3], hsz[5], hsz[4]);
+      }
+    }
+  }
+  const int flags = hsz[7];   // bit 0: pinv TMA variant, bit 1: pinv rollout, bit 2: QP rollout
+  if (st == CLIK_OK && desc->has_pinv) st = setup_kernel(s, "clik_pinv_kernel", &s->pinv);
   if (st == CLIK_OK && desc->has_pinv) {
-    // optional TMA-staged variant (same arguments); absent in images built without it
-    cudaKernel_t probe_tma;
-    if (cudaLibraryGetKernel(&probe_tma, s->lib, "clik_pinv_tma_kernel") == cudaSuccess)
-      st = setup_kernel(s, "clik_pinv_tma_kernel", &s->pinv_tma);
-    else
-      cudaGetLastError();
+    s->pinv.unroll = hsz[6] > 0 ? hsz[6] : 1;
+    s->pinv_reads = ReadMask{(unsigned)hsz[8], (unsigned)hsz[9], (unsigned)hsz[10], (unsigned)hsz[11]};
+    if (flags & 1) st = setup_kernel(s, "clik_pinv_tma_kernel", &s->pinv_tma);
     if (const char* e = getenv("CLIK_TMA")) s->use_tma = atoi(e) != 0;
-    cudaKernel_t probe_ro;
-    if (st == CLIK_OK && cudaLibraryGetKernel(&probe_ro, s->lib, "clik_pinv_rollout_kernel") == cudaSuccess)
-      st = setup_kernel(s, "clik_pinv_rollout_kernel", &s->pinv_rollout);
-    else
-      cudaGetLastError();
+    if (st == CLIK_OK && (flags & 2)) st = setup_kernel(s, "clik_pinv_rollout_kernel", &s->pinv_rollout);
   }
   if (st == CLIK_OK && desc->has_qp) st = setup_kernel(s, "clik_qp_kernel", &s->qp);
   if (st == CLIK_OK && desc->has_qp) {
-    cudaKernel_t probe_qr;
-    if (cudaLibraryGetKernel(&probe_qr, s->lib, "clik_qp_rollout_kernel") == cudaSuccess)
-      st = setup_kernel(s, "clik_qp_rollout_kernel", &s->qp_rollout);
-    else
-      cudaGetLastError();
-  }
-  // the image carries its own sizes: refuse a descriptor that disagrees
-  if (st == CLIK_OK) {
-    cudaKernel_t probe;
-    if (cudaLibraryGetKernel(&probe, s->lib, "clik_sizes_kernel") == cudaSuccess) {
-      int* dsz = nullptr;
-      int hsz[16] = {0};
-      if (cudaMalloc(&dsz, sizeof(hsz)) == cudaSuccess) {
-        void* args[] = {&dsz};
-        cudaError_t le = cudaLaunchKernel((const void*)probe, dim3(1), dim3(1), args, 0, nullptr);
-        if (le == cudaSuccess) le = cudaMemcpy(hsz, dsz, sizeof(hsz), cudaMemcpyDeviceToHost);
-        cudaFree(dsz);
-        if (le != cudaSuccess) {
-          st = fail(CLIK_ERR_CUDA, "size probe failed: %s", cudaGetErrorString(le));
-        } else if ((s->pinv.unroll = hsz[6] > 0 ? hsz[6] : 1),
-                   (s->pinv_reads = ReadMask{(unsigned)hsz[8], (unsigned)hsz[9], (unsigned)hsz[10], (unsigned)hsz[11]}),
-                   (s->qp_reads = ReadMask{(unsigned)hsz[12], (unsigned)hsz[13], (unsigned)hsz[14], (unsigned)hsz[15]}),
-                   hsz[0] != desc->n_robot || hsz[1] != desc->n_virtual || hsz[2] != desc->n_input ||
-                   hsz[3] != desc->n_modes || hsz[4] != desc->qp_n || hsz[5] != desc->qp_m) {
-          st = fail(CLIK_ERR_IMAGE,
-                    "descriptor does not match cubin: image (n_robot %d, n_virtual %d, n_input %d, "
-                    "n_modes %d, qp %dx%d)",
-                    hsz[0], hsz[1], hsz[2], hsz[3], hsz[5], hsz[4]);
-        }
-      }
-    } else {
-      cudaGetLastError();
-    }
+    s->qp_reads = ReadMask{(unsigned)hsz[12], (unsigned)hsz[13], (unsigned)hsz[14], (unsigned)hsz[15]};
+    if (flags & 4) st = setup_kernel(s, "clik_qp_rollout_kernel", &s->qp_rollout);
   }
   if (st != CLIK_OK) {
     cudaLibraryUnload(s->lib);
