@@ -452,6 +452,7 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
                     staged.append((arr, j, "%s[%d]" % (lv, j)))
         t_staged = bool(staged) and staged[0][0] == "t"
         out.append("  static constexpr int NIN = %d;   // input rows read by eval (t first if read)" % len(staged))
+        out.append("  static constexpr bool T_STAGED = %s;" % ("true" if t_staged else "false"))
         out.append("  __device__ static __forceinline__ const double* in_row(int k, long long N, const double* t,")
         out.append("      const double* q, const double* x, const double* y) {")
         out.append("    switch (k) {")
@@ -541,7 +542,9 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out.append("    const double* y, double* qdot, double* xdot, int* mode) {")
         unroll = int(os.environ.get("CLIK_UNROLL", "1"))
         meta["pinv_unroll"] = unroll
-        out.append("  clik::pinv_step<Skill, %d>(N, t, t_stride, q, x, y, qdot, xdot, mode);" % unroll)
+        pf = int(os.environ.get("CLIK_PREFETCH_CTAS", "0"))
+        meta["pinv_prefetch_ctas"] = pf
+        out.append("  clik::pinv_step<Skill, %d, %d>(N, t, t_stride, q, x, y, qdot, xdot, mode);" % (unroll, pf))
         out.append("}")
         out.append('extern "C" __global__ void %s clik_pinv_rollout_kernel(' % bounds)
         out.append("    long long N, int steps, double dt, const double* t0, int t_stride, double* q, double* x,")

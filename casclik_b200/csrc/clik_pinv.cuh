@@ -763,15 +763,28 @@ __device__ __forceinline__ void load_instance(long long N, long long i, const do
   for (int j = 0; j < S::NY; ++j) yv[j] = __ldcs(y + (long long)j * N + i);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // UNROLL instances per thread: the loads of all of them are issued before the first solve, so
 // the memory latency of instance k+1 hides behind the arithmetic of instance k.
-template <class S, int UNROLL>
+// PF > 0: every thread also asks L2 for the inputs of the instance PF CTAs ahead (about one wave
+// of resident CTAs), so that the CTA scheduled there later finds its inputs in L2, not in DRAM.
+template <class S, int UNROLL, int PF = 0>
 __device__ __forceinline__ void pinv_step(long long N, const double* __restrict__ t, int t_stride,
                                           const double* __restrict__ q, const double* __restrict__ x,
                                           const double* __restrict__ y, double* __restrict__ qdot,
                                           double* __restrict__ xdot, int* __restrict__ mode) {
   const long long stride = (long long)gridDim.x * blockDim.x * UNROLL;
   for (long long base = (long long)blockIdx.x * blockDim.x * UNROLL + threadIdx.x; base < N; base += stride) {
+    if constexpr (PF > 0) {
+      const long long ip = base + (long long)PF * blockDim.x * UNROLL;
+      if (ip < N) {
+#pragma unroll
+        for (int k = 0; k < S::NIN; ++k) prefetch_l2(S::in_row(k, N, t, q, x, y) + ((k == 0 && S::T_STAGED && t_stride == 0) ? 0 : ip));
+      }
+    }
     double tv[UNROLL], qv[UNROLL][Max<S::NQ, 1>::v], xv[UNROLL][Max<S::NX, 1>::v], yv[UNROLL][Max<S::NY, 1>::v];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {

@@ -10,14 +10,11 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 scenario = sys.argv[1] if len(sys.argv) > 1 else "ur5_track"
 VARIANTS = [
-    ("plain unroll=1", {"CLIK_TMA": "0"}),
-    ("plain unroll=2 (168 regs, interleaved)", {"CLIK_TMA": "0", "CLIK_UNROLL": "2"}),
-    ("plain unroll=2 minblocks=4 (<=128)", {"CLIK_TMA": "0", "CLIK_UNROLL": "2", "CLIK_MINBLOCKS": "4"}),
-    ("plain unroll=2 minblocks=5 (<=96)", {"CLIK_TMA": "0", "CLIK_UNROLL": "2", "CLIK_MINBLOCKS": "5"}),
-    ("plain unroll=2 minblocks=6 (<=80)", {"CLIK_TMA": "0", "CLIK_UNROLL": "2", "CLIK_MINBLOCKS": "6"}),
-    ("plain unroll=2 block=64 minblocks=10", {"CLIK_TMA": "0", "CLIK_UNROLL": "2", "CLIK_BLOCK": "64", "CLIK_MINBLOCKS": "10"}),
-    ("plain unroll=4 minblocks=5", {"CLIK_TMA": "0", "CLIK_UNROLL": "4", "CLIK_MINBLOCKS": "5"}),
-    ("plain unroll=1 minblocks=7 (<=72)", {"CLIK_TMA": "0", "CLIK_MINBLOCKS": "7"}),
+    ("plain", {}),
+    ("prefetch 512 CTAs ahead", {"CLIK_PREFETCH_CTAS": "512"}),
+    ("prefetch 1036 CTAs ahead", {"CLIK_PREFETCH_CTAS": "1036"}),
+    ("prefetch 2072 CTAs ahead", {"CLIK_PREFETCH_CTAS": "2072"}),
+    ("prefetch 4144 CTAs ahead", {"CLIK_PREFETCH_CTAS": "4144"}),
 ]
 for name, env in VARIANTS:
     e = dict(os.environ)
