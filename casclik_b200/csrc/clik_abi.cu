@@ -1,10 +1,12 @@
 // clik_abi.cu — host side of the C ABI declared in include/clik.h (libclik_b200.so).
 //
 // Loads the per-skill sm_100a cubin emitted by casclik_b200/codegen (CUDA runtime library API:
-// cudaLibraryLoadData / cudaLibraryGetKernel), picks a persistent grid (SM count x resident CTAs),
-// and launches the fused controller-step kernels.  No torch types, no Python; the static CUDA
-// runtime loads libcuda lazily, so the library itself loads on a machine without a GPU and only
-// the entry points that touch a device fail (CLIK_ERR_NOGPU / CLIK_ERR_CUDA).
+// cudaLibraryLoadData / cudaLibraryGetKernel), reads the image's manifest (sizes, optional kernels,
+// input rows read), chooses the launch geometry (one CTA per block of instances; a balanced
+// persistent grid for the opt-in TMA variant) and launches the fused controller-step kernels.
+// No torch types, no Python; the static CUDA runtime loads libcuda lazily, so the library itself
+// loads on a machine without a GPU and only the entry points that touch a device fail
+// (CLIK_ERR_NOGPU / CLIK_ERR_CUDA).
 #include <cuda_runtime.h>
 
 #include <algorithm>

@@ -16,6 +16,8 @@
 // are re-orthogonalised from scratch (modified Gram-Schmidt, at most NX columns) whenever the
 // working set changes: the matrices are tiny (UR5 config: 9 x 15) and it keeps the projection
 // accurate without squaring the condition number.  The iteration count is capped (status 1).
+// (This is the generic dense variant; skills with few dense rows use qp_structured below, which
+// also accepts warm starts.)
 //
 // Outputs per instance: x, status (0 solved, 1 iteration cap, 2 infeasible), and two bit masks
 // of the rows active at their upper / lower bound in the final working set.
@@ -619,7 +621,6 @@ __device__ __forceinline__ void qp_step(long long N, const double* __restrict__ 
     unsigned mu, ml;
     int st;
     if constexpr (S::QSTRUCT) {
-      // the dual method restarts from z = 0: x0 (primal warm start) does not change the answer
       QpSData<S> d;
       S::eval_qps(tv, qv, xv, yv, d);
       // warm start: an explicit working-set guess (active0, may alias `active`) wins over one
