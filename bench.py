@@ -344,8 +344,10 @@ def main():
             "roofline_detail": detail,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
-                    "path": "solve_batch(host arrays) -> clik_*_step_host: pinned host buffers, "
-                            "chunked H2D / kernel / D2H pipeline inside the timed region"},
+                    "path": "solve_batch(host arrays) -> clik_*_step_host with pinned host buffers: the "
+                            "kernel reads inputs from / writes results to mapped host memory over PCIe "
+                            "inside the timed region (pageable buffers would take the chunked H2D / "
+                            "kernel / D2H pipeline instead)"},
             "gpu_launches": args.steps,
             "clocks": clocks,
         }

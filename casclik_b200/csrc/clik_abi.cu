@@ -213,6 +213,25 @@ int64_t host_chunk() {
   return v;
 }
 
+// Page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory()) is mapped into
+// the device address space under UVA.  If every buffer of a host call is such memory, the kernel
+// runs directly on it: the SMs stream the inputs over PCIe and write the results back, both
+// directions at once, with no staging copies (measured 6.4e8 vs 5.6e8 steps/s for the headline
+// skill).  Returns false (-> staged pipeline) for ordinary pageable memory.
+bool device_alias(const void* host, const void** dev) {
+  if (host == nullptr) { *dev = nullptr; return true; }
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;
+  *dev = a.devicePointer;
+  return true;
+}
+
+bool zero_copy_enabled() {
+  static bool v = [] { const char* e = getenv("CLIK_ZERO_COPY"); return e == nullptr || atoi(e) != 0; }();
+  return v;
+}
+
 // copy the rows selected by `mask` as maximal runs of consecutive rows
 template <class Copy>
 clik_status for_row_runs(int rows, unsigned mask, Copy copy) {
@@ -492,6 +511,22 @@ clik_status clik_pinv_step_host(const clik_skill* cs, int64_t N, const double* t
   if (st != CLIK_OK || N == 0) return st;
   if (!qdot) return fail(CLIK_ERR_INVALID, "qdot is required");
   const clik_skill_desc& d = s->desc;
+  if (zero_copy_enabled()) {
+    const void *dt, *dq, *dx, *dy, *dqd, *dxd, *dm;
+    CK(cudaSetDevice(d.device));
+    if (device_alias(t, &dt) && device_alias(q, &dq) && device_alias(d.n_virtual ? x : nullptr, &dx) &&
+        device_alias(d.n_input ? y : nullptr, &dy) && device_alias(qdot, &dqd) &&
+        device_alias(d.n_virtual ? xdot : nullptr, &dxd) && device_alias(mode, &dm)) {
+      std::lock_guard<std::mutex> lock(s->mu);
+      clik_status zs = ensure_scratch(s, 0, 256);
+      if (zs != CLIK_OK) return zs;
+      zs = clik_pinv_step(s, N, (const double*)dt, t_stride, (const double*)dq, (const double*)dx,
+                          (const double*)dy, (double*)dqd, (double*)dxd, (int32_t*)dm, s->scratch.stream[0]);
+      if (zs != CLIK_OK) return zs;
+      CK(cudaStreamSynchronize(s->scratch.stream[0]));
+      return CLIK_OK;
+    }
+  }
   std::vector<Field> f;
   f.push_back({t, nullptr, 1, 8, t_stride ? 1 : 0, 0});
   f.push_back({q, nullptr, d.n_robot, 8, 1, 0});
@@ -524,6 +559,23 @@ clik_status clik_qp_step_host(const clik_skill* cs, int64_t N, const double* t, 
   if (st != CLIK_OK || N == 0) return st;
   if (!sol) return fail(CLIK_ERR_INVALID, "sol is required");
   const clik_skill_desc& d = s->desc;
+  if (zero_copy_enabled()) {
+    const void *dt, *dq, *dx, *dy, *dx0, *da0, *dsol, *dst, *dact;
+    CK(cudaSetDevice(d.device));
+    if (device_alias(t, &dt) && device_alias(q, &dq) && device_alias(d.n_virtual ? x : nullptr, &dx) &&
+        device_alias(d.n_input ? y : nullptr, &dy) && device_alias(x0, &dx0) && device_alias(active0, &da0) &&
+        device_alias(sol, &dsol) && device_alias(status, &dst) && device_alias(active, &dact)) {
+      std::lock_guard<std::mutex> lock(s->mu);
+      clik_status zs = ensure_scratch(s, 0, 256);
+      if (zs != CLIK_OK) return zs;
+      zs = clik_qp_step(s, N, (const double*)dt, t_stride, (const double*)dq, (const double*)dx,
+                        (const double*)dy, (const double*)dx0, (const uint32_t*)da0, (double*)dsol,
+                        (int32_t*)dst, (uint32_t*)dact, max_iter, s->scratch.stream[0]);
+      if (zs != CLIK_OK) return zs;
+      CK(cudaStreamSynchronize(s->scratch.stream[0]));
+      return CLIK_OK;
+    }
+  }
   std::vector<Field> f;
   f.push_back({t, nullptr, 1, 8, t_stride ? 1 : 0, 0});
   f.push_back({q, nullptr, d.n_robot, 8, 1, 0});

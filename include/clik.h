@@ -128,7 +128,10 @@ clik_status clik_qp_dense(int32_t device, int64_t N, int32_t nx, int32_t m, cons
                           double* sol, int32_t* status, uint32_t* active, int32_t max_iter,
                           void* stream);
 
-/* Host-buffer variants (same argument meaning, HOST pointers, synchronous). */
+/* Host-buffer variants (same argument meaning, HOST pointers, synchronous).  Pageable memory goes
+ * through a chunked H2D / kernel / D2H pipeline on internal streams; if every buffer is page-locked
+ * (cudaHostAlloc / cudaHostRegister, torch pin_memory()) the kernel runs directly on the mapped
+ * host memory instead (CLIK_ZERO_COPY=0 disables this). */
 clik_status clik_pinv_step_host(const clik_skill* skill, int64_t N, const double* t,
                                 int32_t t_stride, const double* q, const double* x,
                                 const double* y, double* qdot, double* xdot, int32_t* mode);

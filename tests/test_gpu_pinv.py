@@ -80,6 +80,12 @@ def test_ur5_track_parity_device_and_host_paths():
     # host-buffer ABI (pipelined H2D / kernel / D2H) gives the same bits as the device ABI
     vh, _, mh = ctrl.solve_batch(inp["t"], inp["q"], None, inp["y"])
     assert np.array_equal(vh, v) and np.array_equal(mh, mode)
+    # page-locked host buffers: the kernel runs directly on the mapped host memory (zero copy)
+    torch = _torch()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    out = (pin(np.zeros_like(v)), None, pin(np.zeros_like(mode)))
+    vz, _, mz = ctrl.solve_batch(pin(inp["t"]), pin(inp["q"]), None, pin(inp["y"]), out=out)
+    assert np.array_equal(vz, v) and np.array_equal(mz, mode)
 
 
 def test_ur5_track_single_instance_api_matches_reference_conventions():

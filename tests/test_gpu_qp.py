@@ -78,6 +78,13 @@ def test_ur5_qp_parity_and_kkt():
     sh, sth, ah = ctrl.solve_batch(inp["t"], inp["q"], None, inp["y"])
     assert np.array_equal(sh, sol) and np.array_equal(sth, status)
     assert np.array_equal(ah.astype(np.uint32), active)
+    torch = _torch()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    sz, stz, az = ctrl.solve_batch(pin(inp["t"]), pin(inp["q"]), None, pin(inp["y"]))   # outputs pageable: staged
+    out = (pin(np.zeros_like(sol)), pin(np.zeros_like(status)), pin(np.zeros((2, sol.shape[1]), dtype=np.int32)))
+    sz2, stz2, az2 = ctrl.solve_batch(pin(inp["t"]), pin(inp["q"]), None, pin(inp["y"]), out=out)   # zero copy
+    assert np.array_equal(sz, sol) and np.array_equal(sz2, sol) and np.array_equal(stz2, status)
+    assert np.array_equal(az2.astype(np.uint32), active)
     # warm starts (primal guess as the reference's x0=, or the previous working set) only shorten
     # the iteration: same minimiser (to rounding: the iterates differ), same flags
     sw, stw, aw = _solve_device(ctrl, inp, warm=sol)
