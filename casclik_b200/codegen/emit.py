@@ -371,9 +371,11 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         for b in pinv.blocks:
             row_is_set += [1 if b["kind"] == KIND_SET else 0] * b["rows"]
         out.append(_switch("row_is_set", row_is_set, ret="bool"))
+        out.append("  static constexpr bool CONV_LAST = %s;   // options[\"converge_final_set_to_max\"] applies"
+                   % ("true" if pinv.conv_last else "false"))
         eq_slots, nxt = [], 0
-        for b in pinv.blocks:
-            if b["kind"] in (KIND_EQ, KIND_VELEQ):
+        for bi, b in enumerate(pinv.blocks):
+            if b["kind"] in (KIND_EQ, KIND_VELEQ) or (pinv.conv_last and bi == len(pinv.blocks) - 1):
                 eq_slots.append(nxt)
                 nxt += 1
             else:
@@ -431,6 +433,8 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
                 if b["kind"] in (KIND_EQ, KIND_VELEQ):
                     em.assign("d.des[%d]" % gr, b["des"][r])
                 elif b["kind"] == KIND_SET:
+                    if "des" in b:      # final set with converge_final_set_to_max
+                        em.assign("d.des[%d]" % gr, b["des"][r])
                     em.assign("d.e[%d]" % gr, b["e"][r])
                     em.assign("d.jt[%d]" % gr, b["jt"][r])
                     em.assign("d.smin[%d]" % gr, b["smin"][r])

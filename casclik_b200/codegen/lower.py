@@ -76,11 +76,8 @@ class PinvProgram(object):
         state = spec.robot_var if spec.virtual_var is None else cs.vertcat(spec.robot_var,
                                                                          spec.virtual_var)
         ff = bool(options["feedforward"])
-        if options["converge_final_set_to_max"]:
-            raise NotImplementedError(
-                "converge_final_set_to_max (experimental in the reference, pseudo_inverse.py:337-379) "
-                "is not implemented by the CUDA kernel")
         self.multidim = bool(options["multidim_sets"])
+        self.conv_last = bool(options["converge_final_set_to_max"])
         method = options["pinv_method"]
         if method not in ("damped", "standard"):
             raise ValueError("pinv_method must be 'damped' or 'standard'")
@@ -128,6 +125,25 @@ class PinvProgram(object):
             row += rows
         if not self.blocks:
             raise ValueError("skill has no constraint the pseudo-inverse controller can use")
+        # converge_final_set_to_max (pseudo_inverse.py:337-356): when the LAST constraint is a
+        # SetConstraint and it is active, it also drives its expression to set_max through the
+        # null space of everything above it.  `is_last` in the reference refers to the full
+        # constraint list, so a trailing VelocitySetConstraint switches the option off.
+        last = spec.constraints[-1] if spec.constraints else None
+        self.conv_last = (self.conv_last and last is not None and kind_of(last) == KIND_SET
+                          and self.blocks[-1]["kind"] == KIND_SET)
+        if self.conv_last:
+            if not any(b["kind"] in (KIND_EQ, KIND_VELEQ) for b in self.blocks[:-1]):
+                raise ValueError("converge_final_set_to_max needs an Equality / VelocityEquality constraint "
+                                 "above the final set: with an empty active list the reference fails at "
+                                 "setup (cs.vertcat(*[]), pseudo_inverse.py:343)")
+            b = self.blocks[-1]
+            c = last
+            e = c.expression
+            des = c.gain_times(cs.MX(cs.vertcat(*b["smax"])) - e)
+            if ff:
+                des = des + (-cs.jacobian(e, spec.time_var))
+            b["des"] = des.nodes()
         self.m = row
         self.n_sets = set_idx
         self.max_rows = max(b["rows"] for b in self.blocks)
@@ -138,7 +154,7 @@ class PinvProgram(object):
         self.unit_sets = None
         sets = [b for b in self.blocks if b["kind"] == KIND_SET]
         tasks = [b for b in self.blocks if b["kind"] in (KIND_EQ, KIND_VELEQ)]
-        if sets and len(tasks) == 1 and self.blocks[-1] is tasks[0] and not self.multidim:
+        if sets and len(tasks) == 1 and self.blocks[-1] is tasks[0] and not self.multidim and not self.conv_last:
             info, cols = [], set()
             for b in sets:
                 nz = [(j, n) for j, n in enumerate(b["J"][0]) if n is not dag.ZERO]

@@ -299,7 +299,8 @@ template <class S, int C = 0>
 __device__ __forceinline__ void compute_task_vel(const PinvData<S>& d, TaskVel<S>& tw) {
   if constexpr (C < S::NC) {
     constexpr int kind = S::kind(C);
-    if constexpr (kind == KIND_EQ || kind == KIND_VELEQ) {
+    if constexpr (kind == KIND_EQ || kind == KIND_VELEQ ||
+                  (kind == KIND_SET && S::CONV_LAST && C == S::NC - 1)) {
       constexpr int r0 = S::row0(C);
       constexpr int m = S::rows(C);
       using RC = typename Range<r0, m>::type;
@@ -374,6 +375,23 @@ template <class S, unsigned MASK, int C, class Stack, bool PRE> struct StaticMod
         }
       } else if constexpr (kind == KIND_SET) {
         if constexpr ((MASK >> S::set_index(C)) & 1u) {                   // :399-405
+          if constexpr (S::CONV_LAST && C == S::NC - 1 && Stack::size > 0) {
+            // converge_final_set_to_max (:337-356): the active final set is also driven to
+            // set_max, des = K (max - e) - de/dt, through the null space of everything above it
+            double b[Max<m, 1>::v];
+#pragma unroll
+            for (int a = 0; a < m; ++a) b[a] = d.des[r0 + a];
+            double w[S::NS];
+            if constexpr (PRE) {
+#pragma unroll
+              for (int j = 0; j < S::NS; ++j) w[j] = tw.w[S::eq_index(C)][j];
+            } else {
+              pinv_times<S, RC>(d.J, b, w);
+            }
+            nullspace_apply<S, Stack>(d.J, d.rmask, w);
+#pragma unroll
+            for (int j = 0; j < S::NS; ++j) v[j] += w[j];
+          }
           StaticMode<S, MASK, C + 1, typename Concat<Stack, RC>::type, PRE>::run(d, tw, v);
         } else {
           StaticMode<S, MASK, C + 1, Stack, PRE>::run(d, tw, v);
@@ -467,8 +485,8 @@ __device__ __forceinline__ bool static_mode(const PinvData<S>& d, const TaskVel<
 }
 
 // ---- one mode, mode mask known only at run time (the rare path) -------------------------------------
-// Same algebra with run-time loops over a row list held in local memory.  Only instances whose
-// mode 0 is rejected come here.
+// Same algebra with run-time loops over a row list held in local memory.  Only instances that
+// are rejected by every statically instantiated mode come here.
 template <class S>
 __device__ void dyn_pinv_times(const double* J, const int* rows, int K, const double* b, double* out) {
   constexpr int NS = S::NS;
@@ -562,6 +580,16 @@ __device__ __noinline__ bool dynamic_mode(const PinvData<S>* d, const TaskVel<S>
       }
     } else if (kind == KIND_SET) {
       if ((mask >> S::set_index(c)) & 1u) {
+        if (S::CONV_LAST && c == S::NC - 1 && k > 0) {         // converge_final_set_to_max, :337-356
+          for (int j = 0; j < NS; ++j) w[j] = tw->w[S::eq_index(c)][j];
+          for (int a = 0; a < k; ++a) {
+            double acc = 0.0;
+            for (int j = 0; j < NS; ++j) acc = fma(d->J[stack[a] * NS + j], w[j], acc);
+            b[a] = (S::MULTIDIM && S::row_is_set(stack[a])) ? acc * d->rmask[stack[a]] : acc;
+          }
+          dyn_pinv_times<S>(d->J, stack, k, b, corr);
+          for (int j = 0; j < NS; ++j) v[j] += w[j] - corr[j];
+        }
         for (int a = 0; a < m; ++a) stack[k++] = r0 + a;
       }
     }

@@ -180,8 +180,7 @@ def _mode_velocity(blocks: Sequence[Block], active_bits: Sequence[int], n: int, 
     lam = opts.get("damping_factor", 1e-7)
     conv_last = opts.get("converge_final_set_to_max", False)
     multidim = opts.get("multidim_sets", False)
-    if conv_last:
-        raise NotImplementedError("oracle does not cover converge_final_set_to_max")
+
     dt = blocks[0].J.dtype
     v = np.zeros((N, n), dtype=dt)
     Jlist, rJlist, to_test = [], [], []
@@ -223,6 +222,14 @@ def _mode_velocity(blocks: Sequence[Block], active_bits: Sequence[int], n: int, 
             Jlist.append(b.J)
             rJlist.append(b.J)
         elif b.kind == SET:
+            if active_bits[set_idx] and conv_last and b is blocks[-1]:  # :337-356
+                des = _gain_times(b.gain, _bcast(b.set_max, N, b.rows) - b.e)
+                if ff:
+                    des = des - b.Jt
+                if not Jlist:
+                    raise ValueError("converge_final_set_to_max with an empty active list: the "
+                                     "reference fails at setup (cs.vertcat(*[]), Appendix A16)")
+                v = v + nullspace_term(b.J, des)
             if active_bits[set_idx]:                                   # :399-405
                 Jlist.append(b.J)
                 if multidim:                                           # :289-298, :401-402

@@ -130,8 +130,13 @@ def test_pinv_controller_attributes_and_mode_table():
     with pytest.raises(NotImplementedError):
         cc.PseudoInverseController(multi).setup_problem_functions(load=False)
     cc.PseudoInverseController(multi, options={"multidim_sets": True}).setup_problem_functions(load=False)
-    with pytest.raises(NotImplementedError):
-        cc.PseudoInverseController(multi, options={"converge_final_set_to_max": True}).setup_problem_functions(load=False)
+    # converge_final_set_to_max: only takes effect when the final constraint is a set; it needs a task above
+    cc.PseudoInverseController(multi, options={"multidim_sets": True, "converge_final_set_to_max": True}
+                               ).setup_problem_functions(load=False)
+    tail_set = cc.SkillSpecification("ts", t, q, constraints=[
+        cc.SetConstraint("lim", q[0], set_min=-1.0, set_max=1.0, priority=9)])
+    with pytest.raises(ValueError):
+        cc.PseudoInverseController(tail_set, options={"converge_final_set_to_max": True}).setup_problem_functions(load=False)
 
 
 def test_qp_controller_weights_and_options():

@@ -187,6 +187,30 @@ def test_multidim_sets_option_parity():
     assert np.abs(ref2 - ref_plain).max() > 1e-6          # the option does change the answer
 
 
+def test_converge_final_set_to_max_option_parity():
+    """options["converge_final_set_to_max"] (pseudo_inverse.py:337-356): an active FINAL set is also
+    driven to set_max through the null space of the constraints above it."""
+    t, q = cs.MX.sym("t"), cs.MX.sym("q", 4)
+    reach = cc.EqualityConstraint("reach", cs.vertcat(cs.sin(q[0]) + q[1] - 0.4 * cs.cos(0.2 * t), q[2] * q[3] - 0.1),
+                                  gain=1.5, priority=1)
+    lim = cc.SetConstraint("lim", q[1], set_min=-0.3, set_max=0.35, priority=2)
+    last = cc.SetConstraint("final_set", q[0] + 0.5 * q[3], gain=2.0, set_min=-0.2, set_max=0.25, priority=3)
+    spec = cc.SkillSpecification("conv", t, q, constraints=[last, reach, lim])
+    opts = {"converge_final_set_to_max": True}
+    ctrl = cc.PseudoInverseController(spec, options=dict(opts))
+    ctrl.setup_solver()
+    rng = np.random.default_rng(5)
+    N = 3000
+    inp = {"t": rng.uniform(0, 10, N), "q": rng.uniform(-0.6, 0.6, (4, N))}
+    ref_v, ref_mode = oracle_pinv(spec, inp, dict(opts))
+    v, _, mode = _run_device(ctrl, inp)
+    assert set(np.unique(ref_mode)) >= {0, 1, 2, 3}
+    assert np.array_equal(mode, ref_mode)
+    _assert_parity_multitask(v, spec, inp, opts, "converge_final_set_to_max")
+    plain, _ = oracle_pinv(spec, inp)
+    assert np.abs(plain - ref_v).max() > 1e-3          # the option changes the command
+
+
 def test_no_admissible_mode_returns_zero_and_minus_one():
     # p must stay in [0, 1] but the only task pushes it further out and the set itself cannot
     # produce motion (A5): with p = 2 and target 3 every mode is rejected or ...
