@@ -3,10 +3,20 @@
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may
 import this module.  Nothing under `casclik_b200/` imports it; the product path has no CPU fallback.
 
-PARITY UNPINNED for controller outputs: the reference ships no tests and no golden `solve()`
-vectors, and its arithmetic runs inside CasADi 3.4.1 (requirements.txt:1; `solve` -> Linsol QR,
-`conic` -> bundled qpOASES) and urdf2casadi (no pin), neither of which is in /root/reference or
-installable here.  What *is* pinned, in tests/test_oracle_kat.py:
+PINNING.  The reference ships no tests and no golden `solve()` vectors, and its arithmetic runs
+inside CasADi 3.4.1 (requirements.txt:1; `solve` -> Linsol QR, `conic` -> bundled qpOASES) and
+urdf2casadi (no pin), neither of which is in /root/reference or installable here.
+The oracle is pinned against outputs of the reference's OWN controller code run in the build
+container: tests/golden/make_controller_vectors.py imports the unmodified /root/reference/casclik
+package with a stand-in `casadi` module (casclik_b200.sym evaluated by NumPy; `conic` -> this file's
+QP solver on the reference-built H, A, lba, uba) and drives PseudoInverseController.solve /
+ReactiveQPController.solve one instance at a time on 16 skill/option cases ->
+tests/golden/controller_vectors.json (modes, velocities, QP matrices and minimisers;
+tests/test_golden_controllers.py: modes bit-exact, velocities to ~1e-12).  What that does NOT pin is
+CasADi's and qpOASES' own floating-point arithmetic (they would differ from the stand-in at rounding
+level for the well-conditioned skills; see DESIGN.md §5 for the ill-conditioned ones): in that sense,
+and only in that sense, parity with a CasADi-backed run of the reference remains UNPINNED.
+Also pinned, in tests/test_oracle_kat.py:
   * FK: |p(UR5_home)| = 1.0192 and the home dual quaternion printed in the notebooks;
   * the mode tables produced by running the reference's own create_activation_map
     (pseudo_inverse.py:107-130) with a stub casadi module (tests/golden/activation_maps.json);

@@ -1,0 +1,81 @@
+"""The oracle against tests/golden/controller_vectors.json: outputs of the REFERENCE's own
+PseudoInverseController / ReactiveQPController code (pseudo_inverse.py:259-556, reactive_qp.py:175-540),
+executed unmodified over a stand-in CasADi module by tests/golden/make_controller_vectors.py.
+The skills are rebuilt here with casclik_b200's classes from the same catalogue (golden_skills.py)
+and evaluated on the fixture's inputs."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import casclik_b200 as cc
+from casclik_b200 import cs
+import golden_skills as gs
+from oracle_bridge import oracle_pinv, oracle_qp_problem, orc, close
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "controller_vectors.json")
+with open(GOLDEN) as f:
+    VECTORS = json.load(f)
+NS = gs.Namespace(cs, cc)
+PINV = sorted(n for n, r in VECTORS.items() if r["controller"] == "pinv")
+QP = sorted(n for n, r in VECTORS.items() if r["controller"] == "qp")
+
+
+def load_case(name):
+    rec = VECTORS[name]
+    inp = {k: np.array(v, dtype=np.float64) for k, v in rec["inputs"].items()}
+    spec, inp, kind, kwargs = gs.build(NS, name, inputs=inp)
+    assert kind == rec["controller"] and json.loads(json.dumps(kwargs)) == rec["kwargs"]
+    return spec, inp, kwargs, rec["outputs"]
+
+
+def golden_velocities(outputs):
+    v = np.array([o["robot_vel"] + (o["virtual_vel"] or []) for o in outputs]).T
+    return v, np.array([o["mode"] for o in outputs])
+
+
+def golden_qp(outputs):
+    x = np.array([o["robot_vel"] + (o["virtual_vel"] or []) + (o["slack"] or []) for o in outputs])
+    return (x, np.array(outputs[0]["h"]), np.array([o["A"] for o in outputs]),
+            np.array([o["lb"] for o in outputs]), np.array([o["ub"] for o in outputs]))
+
+
+def qp_weights(kwargs):
+    w = {}
+    if "robot_var_weights" in kwargs:
+        w["w_rob"] = kwargs["robot_var_weights"]
+    if "virtual_var_weights" in kwargs:
+        w["w_virt"] = kwargs["virtual_var_weights"]
+    return w
+
+
+def test_fixture_covers_the_catalogue():
+    assert sorted(VECTORS) == sorted(gs.CASES)
+    modes = set()
+    for n in PINV:
+        modes |= {(n, o["mode"]) for o in VECTORS[n]["outputs"]}
+    assert len({m for n, m in modes if n == "pinv/iiwa_multitask"}) >= 15
+    assert {m for n, m in modes if n == "pinv/conv_last"} == {0, 1, 2, 3}
+
+
+@pytest.mark.parametrize("name", PINV)
+def test_oracle_pinv_reproduces_the_reference_outputs(name):
+    spec, inp, kwargs, outputs = load_case(name)
+    v, mode = oracle_pinv(spec, inp, dict(kwargs.get("options", {})))
+    gv, gmode = golden_velocities(outputs)
+    assert np.array_equal(mode, gmode)
+    assert close(v, gv, 1e-9, 1e-12).all(), np.abs(v - gv).max()
+
+
+@pytest.mark.parametrize("name", QP)
+def test_oracle_qp_matrices_and_solution_reproduce_the_reference(name):
+    spec, inp, kwargs, outputs = load_case(name)
+    h, A, lb, ub = oracle_qp_problem(spec, inp, **qp_weights(kwargs))
+    gx, gh, gA, glb, gub = golden_qp(outputs)
+    assert np.abs(h - gh).max() <= 1e-15
+    assert np.abs(A - gA).max() <= 1e-13
+    assert close(lb, glb, 1e-13, 1e-13).all() and close(ub, gub, 1e-13, 1e-13).all()
+    for i in range(len(outputs)):
+        x, lam, status = orc.solve_qp_single(h, A[i], lb[i], ub[i])
+        assert status == 0 and np.abs(x - gx[i]).max() <= 1e-9 * (1 + np.abs(gx[i]).max())
