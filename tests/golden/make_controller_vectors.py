@@ -100,6 +100,41 @@ def _select(outputs, kind, keep_first=8, per_mode=3, cap=48):
     return sorted(keep[:cap])
 
 
+# closed-loop simulations (the loop of the notebooks around solve(): q += clip(v)*dt, t = t0 + k*dt)
+ROLLOUTS = {"pinv/ur5_moe2016": dict(steps=300, dt=0.008, max_speed=0.6, max_virtual_speed=None, n=4),
+            "pinv/cart_path": dict(steps=200, dt=0.02, max_speed=0.275, max_virtual_speed=0.5, n=4),
+            "pinv/iiwa_multitask": dict(steps=120, dt=0.01, max_speed=1.0, max_virtual_speed=None, n=4),
+            "qp/ur5_qp": dict(steps=80, dt=0.008, max_speed=None, max_virtual_speed=None, n=3)}
+
+
+def _rollout(ctrl, kind, inp, cfg):
+    res = {"config": cfg, "q_final": [], "x_final": [], "last_mode": [], "modes_seen": []}
+    for i in range(cfg["n"]):
+        q = np.array(inp["q"][:, i], dtype=float)
+        x = np.array(inp["x"][:, i], dtype=float) if "x" in inp else None
+        y = _arg(inp.get("y"), i)
+        t0 = float(inp["t"][i])
+        seen = set()
+        for k in range(cfg["steps"]):
+            rv, vv, _ = ctrl.solve(t0 + k * cfg["dt"], q, x, y)
+            v = np.array(sym.DM(rv).full(), dtype=float).reshape(-1)
+            if cfg["max_speed"] is not None:
+                v = np.clip(v, -cfg["max_speed"], cfg["max_speed"])
+            q = q + v * cfg["dt"]
+            if x is not None:
+                w = np.array(sym.DM(vv).full(), dtype=float).reshape(-1)
+                if cfg["max_virtual_speed"] is not None:
+                    w = np.clip(w, -cfg["max_virtual_speed"], cfg["max_virtual_speed"])
+                x = x + w * cfg["dt"]
+            if kind == "pinv":
+                seen.add(int(ctrl.current_mode))
+        res["q_final"].append(q.tolist())
+        res["x_final"].append(None if x is None else x.tolist())
+        res["last_mode"].append(int(ctrl.current_mode) if kind == "pinv" else None)
+        res["modes_seen"].append(sorted(seen))
+    return res
+
+
 out = {}
 for name in sorted(gs.CASES):
     spec, inp, kind, kwargs = gs.build(ns, name)
@@ -123,12 +158,28 @@ for name in sorted(gs.CASES):
                                    "h": m["h"].tolist(), "A": m["A"].tolist(), "lb": m["lb"].tolist(),
                                    "ub": m["ub"].tolist()})
         modes = []
+        # initial-value problem (reactive_qp.py:297-424, :426-459) on the first few instances
+        ctrl.setup_initial_problem_solver()
+        rec["initial"] = []
+        rng = np.random.default_rng(gs.seed_of(name) + 500)
+        for i in range(6):
+            dq0 = rng.uniform(-0.3, 0.3, inp["q"].shape[0])
+            virt, slack = ctrl.solve_initial_problem(float(inp["t"][i]), _arg(inp["q"], i), _arg(inp.get("x"), i),
+                                                     dq0, _arg(inp.get("y"), i))
+            m = _CpuConic.last
+            rec["initial"].append({"dq0": dq0.tolist(), "virtual": _vec(virt), "slack": _vec(slack),
+                                   "h": m["h"].tolist(), "A": m["A"].tolist(), "lb": m["lb"].tolist(),
+                                   "ub": m["ub"].tolist()})
     keep = _select(rec["outputs"], kind)
     rec["outputs"] = [rec["outputs"][i] for i in keep]
     rec["inputs"] = {k: (np.asarray(v)[keep] if np.ndim(v) == 1 else np.asarray(v)[:, keep]).tolist()
                      for k, v in inp.items()}
     if kind == "pinv":
         modes = sorted(set(o["mode"] for o in rec["outputs"]))
+    if name in ROLLOUTS:
+        kept = {k: np.array(v, dtype=float) for k, v in rec["inputs"].items()}
+        rec["rollout"] = _rollout(ctrl, kind, kept, ROLLOUTS[name])
+        print("   rollout: modes seen", rec["rollout"]["modes_seen"])
     out[name] = rec
     print("%-42s %3d of %d instances kept  modes %s" % (name, len(keep), N, modes))
 

@@ -79,3 +79,28 @@ def test_oracle_qp_matrices_and_solution_reproduce_the_reference(name):
     for i in range(len(outputs)):
         x, lam, status = orc.solve_qp_single(h, A[i], lb[i], ub[i])
         assert status == 0 and np.abs(x - gx[i]).max() <= 1e-9 * (1 + np.abs(gx[i]).max())
+
+
+def initial_args(spec, inp, rec, i):
+    ini = rec["initial"][i]
+    col = lambda k: None if k not in inp else inp[k][:, i]
+    return ini, (float(inp["t"][i]), inp["q"][:, i], col("x"), np.array(ini["dq0"]), col("y"))
+
+
+@pytest.mark.parametrize("name", QP)
+def test_initial_value_problem_matrices_reproduce_the_reference(name):
+    """reactive_qp.py:297-424: H, A, lb, ub of the slack / virtual-variable initial problem (the
+    matrices are host-side expression evaluation; the solve itself is checked on the GPU)."""
+    spec, inp, kwargs, outputs = load_case(name)
+    ctrl = cc.ReactiveQPController(spec, **kwargs)
+    ctrl.setup_initial_problem_solver()
+    assert ctrl._has_initial
+    ip = ctrl._initial
+    for i in range(len(VECTORS[name]["initial"])):
+        ini, (t, q, x, dq, y) = initial_args(spec, inp, VECTORS[name], i)
+        vals = [t, q, dq] + ([x] if spec._has_virtual else []) + ([y] if spec._has_input else [])
+        H, A, lb, ub = (np.asarray(ip.funcs[k](*vals).toarray()) for k in ("H", "A", "Blb", "Bub"))
+        assert np.abs(np.diag(H) - np.array(ini["h"])).max() <= 1e-15 and np.count_nonzero(H - np.diag(np.diag(H))) == 0
+        assert np.abs(A - np.array(ini["A"])).max() <= 1e-13
+        assert close(lb.reshape(-1), np.array(ini["lb"]), 1e-13, 1e-13).all()
+        assert close(ub.reshape(-1), np.array(ini["ub"]), 1e-13, 1e-13).all()

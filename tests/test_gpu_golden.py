@@ -57,3 +57,53 @@ def test_qp_kernel_reproduces_the_reference_problem_and_its_minimiser(name):
         assert abs(obj - gobj) <= 1e-6 * (1 + abs(gobj))
         kk = orc.kkt_residuals(gh, gA[i], glb[i], gub[i], sol[i])      # against the REFERENCE-built matrices
         assert kk["primal"] < 1e-6 and kk["stationarity"] < 1e-6 and kk["sign"] < 1e-6
+
+
+@pytest.mark.parametrize("name", QP)
+def test_initial_value_problem_reproduces_the_reference(name):
+    from test_golden_controllers import VECTORS, initial_args
+    spec, inp, kwargs, outputs = load_case(name)
+    ctrl = cc.ReactiveQPController(spec, **kwargs)
+    ctrl.setup_initial_problem_solver()
+    for i in range(len(VECTORS[name]["initial"])):
+        ini, (t, q, x, dq, y) = initial_args(spec, inp, VECTORS[name], i)
+        virt, slack = ctrl.solve_initial_problem(t, q, x, dq, y)
+        for got, want in ((virt, ini["virtual"]), (slack, ini["slack"])):
+            if want is None:
+                assert got is None
+            else:
+                g, w = np.asarray(got.toarray()).reshape(-1), np.array(want)
+                assert np.abs(g - w).max() <= 1e-7 * (1 + np.abs(w).max())
+
+
+@pytest.mark.parametrize("name", sorted(n for n in PINV + QP if "rollout" in
+                                        __import__("test_golden_controllers").VECTORS[n]))
+def test_device_rollout_reproduces_the_reference_simulation_loop(name):
+    """The notebooks' loop around the reference's solve() (q += clip(v)*dt for `steps` steps, run by
+    the generator with the reference controllers) against ONE clik_*_rollout launch."""
+    import torch
+    from test_golden_controllers import VECTORS
+    spec, inp, kwargs, outputs = load_case(name)
+    ro = VECTORS[name]["rollout"]
+    cfg, n = ro["config"], ro["config"]["n"]
+    qp = VECTORS[name]["controller"] == "qp"
+    ctrl = (cc.ReactiveQPController if qp else cc.PseudoInverseController)(spec, **kwargs)
+    if qp:
+        ctrl.setup_problem_functions()
+    ctrl.setup_solver()
+    put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    q = put(inp["q"][:, :n])
+    x = put(inp["x"][:, :n]) if "x" in inp else None
+    y = put(inp["y"][:, :n]) if "y" in inp else None
+    out = ctrl.rollout_batch(put(inp["t"][:n]), q, cfg["steps"], cfg["dt"], virtual_var=x, input_var=y,
+                             max_speed=cfg["max_speed"], max_virtual_speed=cfg["max_virtual_speed"])
+    assert int(out["n_failed"].sum()) == 0
+    want = np.array(ro["q_final"]).T
+    got = q.cpu().numpy()
+    # a closed loop contracts errors along the task and integrates them elsewhere: 1e-7 over 80-300 steps
+    assert np.abs(got - want).max() <= 1e-7 * (1 + np.abs(want).max()), np.abs(got - want).max()
+    assert np.abs(got - inp["q"][:, :n]).max() > 1e-2          # the state did move
+    if x is not None:
+        assert np.abs(x.cpu().numpy() - np.array(ro["x_final"]).T).max() <= 1e-7
+    if not qp:
+        assert out["mode"].cpu().numpy().tolist() == ro["last_mode"]
