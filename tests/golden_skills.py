@@ -173,7 +173,15 @@ def ur5_qp(ns, rng, N):
                                      set_min=-cs.vertcat([max_speed] * 6), set_max=cs.vertcat([max_speed] * 6))
     spec = ns.SkillSpecification(label="ur5_qp", time_var=t, robot_var=q, robot_vel_var=dq, input_var=y,
                                  constraints=[c_pos, c_lim, c_spd])
-    return spec, {"t": np.zeros(N), "q": _ur5_q(rng, N), "y": rng.uniform(-0.5, 0.5, (3, N))}
+    qs, ys = _ur5_q(rng, N), rng.uniform(-0.5, 0.5, (3, N))
+    # the first instances start a few millimetres from their target: the regime the notebook's closed
+    # loop runs in (K = 50, dt = 8 ms).  Far targets saturate every speed limit and the weakly coupled
+    # wrist joints go bang-bang, where a 1e-12 perturbation moves a switching time by a whole step —
+    # fine for single steps, useless as a closed-loop known answer.
+    p_fk = cs.Function("p_fk", [q], [p])
+    for i in range(4):
+        ys[:, i] = np.asarray(p_fk(qs[:, i]).toarray()).reshape(-1) + rng.uniform(-0.004, 0.004, 3)
+    return spec, {"t": np.zeros(N), "q": qs, "y": ys}
 
 
 def cart_path_qp(ns, rng, N):
