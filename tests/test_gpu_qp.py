@@ -172,12 +172,20 @@ def test_infeasible_and_iteration_cap_are_status_flags():
     assert np.all(status == runtime.QP_INFEASIBLE)
     with pytest.raises(RuntimeError):
         ctrl.solve(0.0, 0.0)
-    sc = scenarios.get("ur5_qp")
+    # iteration cap (the generic solver starts cold: one iteration is not enough for the Moe-2016 QP;
+    # the structured solver's crash start usually needs a single certifying iteration)
+    sc = scenarios.get("ur5_moe2016_qp")
     c2 = sc.make_controller()
     c2.setup_problem_functions()
     inp = sc.sample(64, seed=0)
-    _, st, _ = c2.solve_batch(inp["t"], inp["q"], None, inp["y"], max_iter=1)
+    _, st, _ = c2.solve_batch(inp["t"], inp["q"], None, None, max_iter=1)
     assert np.all((st == runtime.QP_MAXITER) | (st == runtime.QP_SOLVED)) and (st == runtime.QP_MAXITER).any()
+    sc = scenarios.get("ur5_qp")
+    c3 = sc.make_controller()
+    c3.setup_problem_functions()
+    inp = sc.sample(64, seed=0)
+    _, st, _ = c3.solve_batch(inp["t"], inp["q"], None, inp["y"], max_iter=1)
+    assert np.all((st == runtime.QP_MAXITER) | (st == runtime.QP_SOLVED))
 
 
 def test_conic_object_dense_random_problems():

@@ -25,6 +25,8 @@ static inline void __stcs(double* p, double v) { *p = v; }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline unsigned __activemask() { return 1u; }
+static inline int __any_sync(unsigned, int p) { return p; }
 using std::fma; using std::fmax; using std::fmin; using std::fabs; using std::sqrt;
 #include "%s"
 extern "C" int host_qp(int nx, int m, double* A, const double* lb, const double* ub, const double* h,
@@ -150,6 +152,13 @@ struct S {
   static constexpr int unit_col(int i) { constexpr int t[7] = {0, 1, 2, 0, 3, 5, 1}; return t[i]; }
   static constexpr double unit_coef(int i) { constexpr double t[7] = {1.0, 1.0, -1.0, 2.0, 1.0, -0.5, 1.0}; return t[i]; }
 };
+extern "C" void host_crash(const double* Ad, const double* lbd, const double* ubd, const double* lbu,
+                           const double* ubu, const double* s, unsigned* wu, unsigned* wl) {
+  clik::QpSData<S> d;
+  std::memcpy(d.Ad, Ad, sizeof(d.Ad)); std::memcpy(d.lbd, lbd, sizeof(d.lbd)); std::memcpy(d.ubd, ubd, sizeof(d.ubd));
+  std::memcpy(d.lbu, lbu, sizeof(d.lbu)); std::memcpy(d.ubu, ubu, sizeof(d.ubu)); std::memcpy(d.s, s, sizeof(d.s));
+  clik::crash_guess<S>(d, wu, wl);
+}
 extern "C" int host_qps(const double* Ad, const double* lbd, const double* ubd, const double* lbu,
                         const double* ubu, const double* s, double* x, unsigned* au, unsigned* al, int max_iter,
                         unsigned wu, unsigned wl) {
@@ -186,6 +195,15 @@ def host_qps(tmp_path_factory):
                           x.ctypes.data_as(ctypes.c_void_p), ctypes.byref(au), ctypes.byref(al), max_iter,
                           ctypes.c_uint(warm[0]), ctypes.c_uint(warm[1]))
         return x, st, au.value, al.value
+
+    def crash(h, A, lb, ub):
+        ur = [r for r, _, _ in UNIT]
+        arrs = [A[DENSE_ROWS], lb[DENSE_ROWS], ub[DENSE_ROWS], lb[ur], ub[ur], 1.0 / np.sqrt(h)]
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
+        wu, wl = ctypes.c_uint(), ctypes.c_uint()
+        lib.host_crash(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs], ctypes.byref(wu), ctypes.byref(wl))
+        return wu.value, wl.value
+    solve.crash = crash
     return solve
 
 
@@ -274,3 +292,34 @@ def test_structured_solver_warm_start_never_changes_the_answer(host_qps):
             assert kk["primal"] < 1e-9 and kk["stationarity"] < 1e-9 and kk["sign"] < 1e-9, (trial, g, kk)
             assert (auw, alw) == (au, al), (trial, g)
     assert n_warm_ok > 1000
+
+
+def test_crash_start_guess_is_sound_and_never_changes_the_answer(host_qps):
+    """The working-set guess used for cold solves (crash_guess: primal-dual active-set passes over
+    equality + single-variable rows): every equality row on one side, at most one single-variable row
+    per column; started from it the solver returns the cold-start answer and flags; and for most
+    problems it already IS the final working set."""
+    rng = np.random.default_rng(33)
+    n_guess, n_ok, n_exact = 0, 0, 0
+    for trial in range(400):
+        h, A, lb, ub = _structured_problem(rng, eq_prob=3.0 if trial % 2 else 0.3, tight=(trial % 3 == 0))
+        x, st, au, al = host_qps(h, A, lb, ub)
+        wu, wl = host_qps.crash(h, A, lb, ub)
+        assert wu & wl == 0
+        for r in DENSE_ROWS:
+            assert (wu | wl) >> r & 1 or lb[r] != ub[r]                   # every equality row is held
+        cols = [c for r, c, k in UNIT if (wu | wl) >> r & 1]
+        assert len(cols) == len(set(cols))                                # one fixed row per variable
+        for r in range(9):                                                # never a row without that bound
+            assert not ((wu >> r & 1) and not np.isfinite(ub[r])) and not ((wl >> r & 1) and not np.isfinite(lb[r]))
+        if st != 0:
+            continue
+        n_guess += 1
+        xw, stw, auw, alw = host_qps(h, A, lb, ub, warm=(wu, wl))
+        if stw != 0:
+            continue                                     # the kernels retry cold
+        n_ok += 1
+        assert np.abs(xw - x).max() < 1e-9 * (1 + np.abs(x).max()), trial
+        assert (auw, alw) == (au, al), trial
+        n_exact += int((wu | wl) == (au | al))
+    assert n_ok > 0.95 * n_guess and n_exact > 0.8 * n_guess, (n_guess, n_ok, n_exact)
