@@ -492,7 +492,7 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out.append("  static constexpr int QN = %d, QM = %d;" % (qp.nx, qp.m))
         md, mu = len(qp.dense_rows), len(qp.unit_rows)
         env = os.environ.get("CLIK_QP_STRUCT")
-        qstruct = (md <= 4 and qp.nx <= 12 and qp.m <= 32) if env is None else (env == "1")
+        qstruct = (md <= 6 and qp.nx <= 12 and qp.m <= 32) if env is None else (env == "1")
         meta["qp_structured"] = qstruct
         meta["qp_dense_rows"], meta["qp_unit_rows"] = md, mu
         out.append("  static constexpr bool QSTRUCT = %s;   // register-resident structured solver" %

@@ -605,18 +605,34 @@ __device__ __forceinline__ void masks_from_x0(const QpSData<S>& D, const double 
 // certifies the result, so the answer never depends on it.
 constexpr int CRASH_PASSES = 8;
 template <class S>
-__device__ __forceinline__ void crash_guess(const QpSData<S>& D, unsigned* up, unsigned* lo) {
+__device__ __forceinline__ void crash_guess(const QpSData<S>& D, unsigned* up /*in: guess, out*/,
+                                            unsigned* lo) {
   constexpr int NX = S::QN, MD = S::QMD, MU = S::QMU, MD1 = MD > 0 ? MD : 1;
   bool eq[MD1];
   double s2[NX], yv[MD1];
   int fr[NX];                        // +(i+1) / -(i+1): variable fixed by unit row i at its upper / lower bound
   int da[MD1];                       // dense row held at its upper (+1) / lower (-1) bound, 0 = not held
+  // the caller's guess (the previous step's working set in a rollout, or nothing) seeds the iteration:
+  // an unchanged set is confirmed by the first pass
+  const unsigned gu = *up, gl = *lo;
 #pragma unroll
   for (int j = 0; j < NX; ++j) { s2[j] = D.s[j] * D.s[j]; fr[j] = 0; }
+#pragma unroll
+  for (int i = 0; i < MU; ++i) {
+    const int c = S::unit_col(i);
+    if (S::unit_row(i) < 32 && fr[c] == 0) {
+      if (((gu >> S::unit_row(i)) & 1u) && fabs(D.ubu[i]) < INFINITY) fr[c] = i + 1;
+      else if (((gl >> S::unit_row(i)) & 1u) && fabs(D.lbu[i]) < INFINITY) fr[c] = -(i + 1);
+    }
+  }
 #pragma unroll
   for (int a = 0; a < MD; ++a) {
     eq[a] = (D.lbd[a] == D.ubd[a]) && (fabs(D.ubd[a]) < INFINITY) && S::dense_row(a) < 32;
     da[a] = eq[a] ? 1 : 0;
+    if (S::dense_row(a) < 32 && !eq[a]) {
+      if (((gu >> S::dense_row(a)) & 1u) && fabs(D.ubd[a]) < INFINITY) da[a] = 1;
+      else if (((gl >> S::dense_row(a)) & 1u) && fabs(D.lbd[a]) < INFINITY) da[a] = -1;
+    }
     yv[a] = 0.0;
   }
 #pragma unroll 1
@@ -796,15 +812,14 @@ __device__ __forceinline__ void qp_step(long long N, const double* __restrict__ 
 #pragma unroll
         for (int j = 0; j < S::QN; ++j) x0v[j] = x0[(long long)j * N + i];
         masks_from_x0<S>(d, x0v, &wu, &wl);
-      } else if (S::QP_CRASH) {
-        crash_guess<S>(d, &wu, &wl);
-      } else if (S::QP_EQ_START) {
+      } else if (!S::QP_CRASH && S::QP_EQ_START) {
         // no guess: equality rows are active at every solution, start with them held
 #pragma unroll
         for (int a = 0; a < S::QMD; ++a) {
           if (S::dense_row(a) < 32 && d.lbd[a] == d.ubd[a]) wu |= 1u << S::dense_row(a);
         }
       }
+      if (S::QP_CRASH) crash_guess<S>(d, &wu, &wl);     // predicts the working set from any guess, or none
       st = QP_MAXITER;
 #pragma unroll 1
       for (int attempt = 0; attempt < 2; ++attempt) {   // a bad guess must never cost the answer:
@@ -858,7 +873,7 @@ __device__ __forceinline__ void qp_rollout(long long N, int steps, double dt, co
         QpSData<S> d;
         S::eval_qps(tv, qv, xv, yv, d);
         unsigned wu = mu, wl = ml;
-        if (S::QP_CRASH && (wu | wl) == 0u) crash_guess<S>(d, &wu, &wl);   // first step: no previous set
+        if (S::QP_CRASH) crash_guess<S>(d, &wu, &wl);   // previous step's set -> this step's (usually one pass)
         st = QP_MAXITER;
 #pragma unroll 1
         for (int attempt = 0; attempt < 2; ++attempt) {

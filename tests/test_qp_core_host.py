@@ -153,7 +153,7 @@ struct S {
   static constexpr double unit_coef(int i) { constexpr double t[7] = {1.0, 1.0, -1.0, 2.0, 1.0, -0.5, 1.0}; return t[i]; }
 };
 extern "C" void host_crash(const double* Ad, const double* lbd, const double* ubd, const double* lbu,
-                           const double* ubu, const double* s, unsigned* wu, unsigned* wl) {
+                           const double* ubu, const double* s, unsigned* wu /*in/out*/, unsigned* wl) {
   clik::QpSData<S> d;
   std::memcpy(d.Ad, Ad, sizeof(d.Ad)); std::memcpy(d.lbd, lbd, sizeof(d.lbd)); std::memcpy(d.ubd, ubd, sizeof(d.ubd));
   std::memcpy(d.lbu, lbu, sizeof(d.lbu)); std::memcpy(d.ubu, ubu, sizeof(d.ubu)); std::memcpy(d.s, s, sizeof(d.s));
@@ -196,11 +196,11 @@ def host_qps(tmp_path_factory):
                           ctypes.c_uint(warm[0]), ctypes.c_uint(warm[1]))
         return x, st, au.value, al.value
 
-    def crash(h, A, lb, ub):
+    def crash(h, A, lb, ub, seed=(0, 0)):
         ur = [r for r, _, _ in UNIT]
         arrs = [A[DENSE_ROWS], lb[DENSE_ROWS], ub[DENSE_ROWS], lb[ur], ub[ur], 1.0 / np.sqrt(h)]
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
-        wu, wl = ctypes.c_uint(), ctypes.c_uint()
+        wu, wl = ctypes.c_uint(seed[0]), ctypes.c_uint(seed[1])
         lib.host_crash(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs], ctypes.byref(wu), ctypes.byref(wl))
         return wu.value, wl.value
     solve.crash = crash
@@ -322,4 +322,12 @@ def test_crash_start_guess_is_sound_and_never_changes_the_answer(host_qps):
         assert np.abs(xw - x).max() < 1e-9 * (1 + np.abs(x).max()), trial
         assert (auw, alw) == (au, al), trial
         n_exact += int((wu | wl) == (au | al))
+        # seeded with the solution's set it confirms it; seeded with garbage it is still a sound guess
+        assert host_qps.crash(h, A, lb, ub, seed=(au, al)) == (au, al) or (wu | wl) != (au | al)
+        gu = int(rng.integers(0, 512))
+        su, sl = host_qps.crash(h, A, lb, ub, seed=(gu, int(rng.integers(0, 512)) & ~gu))
+        assert su & sl == 0
+        xs, sts, aus, als = host_qps(h, A, lb, ub, warm=(su, sl))
+        if sts == 0:
+            assert np.abs(xs - x).max() < 1e-9 * (1 + np.abs(x).max()) and (aus, als) == (au, al), trial
     assert n_ok > 0.95 * n_guess and n_exact > 0.8 * n_guess, (n_guess, n_ok, n_exact)
