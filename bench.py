@@ -193,9 +193,15 @@ def main():
                          "use --impl reference for the CPU baseline")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        if os.environ.get("CLIK_NUMA_BIND", "1") == "1":
+            # one process per GPU: keep each rank (and the pinned host buffers of its e2e leg) on the
+            # socket its GPU hangs off.  Not at N = 1, where the cpu_baseline leg wants every host core.
+            from casclik_b200 import sharding
+            numa = sharding.bind_to_device_numa_node(local)
 
     def barrier():
         if world > 1:
@@ -234,11 +240,30 @@ def main():
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
+    # The K timed steps are K launches of the step kernel through the C ABI.  They are captured once
+    # into a CUDA graph and replayed, so that host jitter (8 ranks sharing the box's cores with the
+    # clock samplers) cannot turn a 29 us kernel into a launch-bound loop; same kernels, same inputs.
+    graph = None
+    if os.environ.get("CLIK_BENCH_GRAPH", "1") == "1":
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(args.steps):
+                    step(i)
+            g.replay()                       # untimed: uploads the graph
+            graph = g
+        except Exception as exc:             # capture not possible: time the plain launch loop
+            sys.stderr.write("bench: CUDA graph capture failed (%s); timing direct launches\n" % exc)
+            graph = None
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for i in range(args.steps):
-        step(i)
+    if graph is not None:
+        graph.replay()
+    else:
+        for i in range(args.steps):
+            step(i)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -337,6 +362,10 @@ def main():
             "config": {"workload": scenario.description, "scenario": scenario.name,
                        "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": "independent shards, one per GPU, no collective on the data path",
+                       "launch_mode": ("%d step-kernel launches replayed from one CUDA graph" % args.steps
+                                       if graph is not None else "direct launches"),
+                       "host_affinity": ("rank 0 bound to its GPU's NUMA node: %d of %d CPUs" % (len(numa[1]), len(numa[0]))
+                                         if numa else "unbound"),
                        "l2": "rotating %d resident input sets (%d MB total) > 126 MB L2"
                              % (args.sets, args.sets * bytes_step * B // (1 << 20)),
                        "launch": _launch_info(ctrl, is_qp)},

@@ -34,3 +34,31 @@ def gather_columns(local, n_total, device=None):
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad)
     return torch.cat([p[:, :hi - lo] for p, (lo, hi) in zip(parts, sizes)], dim=1)
+
+
+def bind_to_device_numa_node(device_index):
+    """Pin the calling process to the CPUs next to CUDA device `device_index` (NVML's ideal-CPU set
+    for that GPU), so that page-locked host buffers allocated afterwards (first touch) and the
+    zero-copy traffic of the host entry points stay on the GPU's own socket.  With one process per
+    GPU this keeps 8 ranks from pulling each other's host buffers across the socket interconnect.
+    Returns (previous affinity, new affinity) or None if NVML / the platform does not allow it."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            props = torch.cuda.get_device_properties(device_index)
+            bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        before = sorted(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        after = sorted(os.sched_getaffinity(0))
+        if not after:
+            os.sched_setaffinity(0, before)
+            return None
+        return before, after
+    except Exception:
+        return None
