@@ -502,6 +502,8 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
             out.append("  static constexpr int QMD = %d, QMU = %d;   // dense rows, single-variable rows" % (md, mu))
             out.append("  static constexpr bool QP_CRASH = %s;   // closed-form working-set guess for cold solves" %
                        ("true" if os.environ.get("CLIK_QP_CRASH", "1") == "1" else "false"))
+            out.append("  static constexpr bool QP_CRASH_FINAL = %s;   // a certified prediction is returned as is" %
+                       ("true" if os.environ.get("CLIK_QP_CRASH_FINAL", "1") == "1" else "false"))
             out.append("  static constexpr bool QP_EQ_START = %s;" %
                        ("true" if os.environ.get("CLIK_QP_EQ_START", "0") == "1" else "false"))
             out.append(_switch("dense_row", qp.dense_rows or [0]))

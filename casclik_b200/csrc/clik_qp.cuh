@@ -605,8 +605,8 @@ __device__ __forceinline__ void masks_from_x0(const QpSData<S>& D, const double 
 // certifies the result, so the answer never depends on it.
 constexpr int CRASH_PASSES = 8;
 template <class S>
-__device__ __forceinline__ void crash_guess(const QpSData<S>& D, unsigned* up /*in: guess, out*/,
-                                            unsigned* lo) {
+__device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*in: guess, out*/,
+                                            unsigned* lo, double (&xout)[S::QN]) {
   constexpr int NX = S::QN, MD = S::QMD, MU = S::QMU, MD1 = MD > 0 ? MD : 1;
   bool eq[MD1];
   double s2[NX], yv[MD1];
@@ -635,6 +635,7 @@ __device__ __forceinline__ void crash_guess(const QpSData<S>& D, unsigned* up /*
     }
     yv[a] = 0.0;
   }
+  bool certified = false;            // this thread's set stopped changing and its face optimum passes the KKT check
 #pragma unroll 1
   for (int pass = 0; pass < CRASH_PASSES; ++pass) {
     double xf[NX], w[NX];            // value of a fixed variable (0 if free); 1/h_j of a free one (0 if fixed)
@@ -735,10 +736,14 @@ __device__ __forceinline__ void crash_guess(const QpSData<S>& D, unsigned* up /*
     // dense inequality rows: keep while the multiplier (-y for upper, +y for lower) is non-negative,
     // take up when the face optimum violates them (equality rows always stay)
 #pragma unroll
+    bool held_ok = true;             // every held dense row really sits on its bound (the Gram solve was accurate)
+#pragma unroll
     for (int a = 0; a < MD; ++a) {
       double r = 0.0;
 #pragma unroll
       for (int j = 0; j < NX; ++j) r = fma(D.Ad[a * NX + j], xc[j], r);
+      const double bnd = (da[a] < 0) ? D.lbd[a] : D.ubd[a];
+      held_ok = held_ok && (da[a] == 0 || fabs(r - bnd) <= 1e-11 * (1.0 + fabs(bnd)));
       int na = (da[a] > 0 && yv[a] <= 0.0) ? 1 : ((da[a] < 0 && yv[a] >= 0.0) ? -1 : 0);
       if (da[a] == 0 && S::dense_row(a) < 32) {
         if (r - D.ubd[a] > 1e-12 * fmax(1.0, fabs(D.ubd[a]))) na = 1;
@@ -748,6 +753,11 @@ __device__ __forceinline__ void crash_guess(const QpSData<S>& D, unsigned* up /*
       changed = changed || (na != da[a]);
       da[a] = na;
     }
+    // unchanged set = every row feasible, every multiplier of the right sign: the face optimum is the
+    // minimiser.  (A later pass of a thread that waits for its warp recomputes the same numbers.)
+    certified = !changed && held_ok;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) xout[j] = xc[j];
     if (!__any_sync(__activemask(), changed)) break;
   }
   unsigned mu = 0u, ml = 0u;
@@ -767,6 +777,7 @@ __device__ __forceinline__ void crash_guess(const QpSData<S>& D, unsigned* up /*
   }
   *up = mu;
   *lo = ml;
+  return certified;
 }
 
 // Everything S::eval_qp produces for one instance.
@@ -819,10 +830,15 @@ __device__ __forceinline__ void qp_step(long long N, const double* __restrict__ 
           if (S::dense_row(a) < 32 && d.lbd[a] == d.ubd[a]) wu |= 1u << S::dense_row(a);
         }
       }
-      if (S::QP_CRASH) crash_guess<S>(d, &wu, &wl);     // predicts the working set from any guess, or none
-      st = QP_MAXITER;
+      // predicts the working set from any guess, or none; when the prediction certifies itself its
+      // face optimum is the answer and the iteration below is skipped
+      bool solved = false;
+      if (S::QP_CRASH) solved = crash_guess<S>(d, &wu, &wl, xs) && S::QP_CRASH_FINAL;
+      st = solved ? QP_OK : QP_MAXITER;
+      mu = wu;
+      ml = wl;
 #pragma unroll 1
-      for (int attempt = 0; attempt < 2; ++attempt) {   // a bad guess must never cost the answer:
+      for (int attempt = 0; attempt < 2 && !solved; ++attempt) {   // a bad guess must never cost the answer:
         if (attempt > 0) {                              // second attempt = cold start
           wu = wl = 0u;
           S::eval_qps(tv, qv, xv, yv, d);
@@ -873,10 +889,12 @@ __device__ __forceinline__ void qp_rollout(long long N, int steps, double dt, co
         QpSData<S> d;
         S::eval_qps(tv, qv, xv, yv, d);
         unsigned wu = mu, wl = ml;
-        if (S::QP_CRASH) crash_guess<S>(d, &wu, &wl);   // previous step's set -> this step's (usually one pass)
-        st = QP_MAXITER;
+        bool solved = false;            // previous step's set -> this step's (usually one pass)
+        if (S::QP_CRASH) solved = crash_guess<S>(d, &wu, &wl, xs) && S::QP_CRASH_FINAL;
+        st = solved ? QP_OK : QP_MAXITER;
+        if (solved) { mu = wu; ml = wl; }
 #pragma unroll 1
-        for (int attempt = 0; attempt < 2; ++attempt) {
+        for (int attempt = 0; attempt < 2 && !solved; ++attempt) {
           if (attempt > 0) {
             wu = wl = 0u;
             S::eval_qps(tv, qv, xv, yv, d);

@@ -152,12 +152,15 @@ struct S {
   static constexpr int unit_col(int i) { constexpr int t[7] = {0, 1, 2, 0, 3, 5, 1}; return t[i]; }
   static constexpr double unit_coef(int i) { constexpr double t[7] = {1.0, 1.0, -1.0, 2.0, 1.0, -0.5, 1.0}; return t[i]; }
 };
-extern "C" void host_crash(const double* Ad, const double* lbd, const double* ubd, const double* lbu,
-                           const double* ubu, const double* s, unsigned* wu /*in/out*/, unsigned* wl) {
+extern "C" int host_crash(const double* Ad, const double* lbd, const double* ubd, const double* lbu,
+                          const double* ubu, const double* s, unsigned* wu /*in/out*/, unsigned* wl, double* x) {
   clik::QpSData<S> d;
   std::memcpy(d.Ad, Ad, sizeof(d.Ad)); std::memcpy(d.lbd, lbd, sizeof(d.lbd)); std::memcpy(d.ubd, ubd, sizeof(d.ubd));
   std::memcpy(d.lbu, lbu, sizeof(d.lbu)); std::memcpy(d.ubu, ubu, sizeof(d.ubu)); std::memcpy(d.s, s, sizeof(d.s));
-  clik::crash_guess<S>(d, wu, wl);
+  double xs[S::QN];
+  const bool certified = clik::crash_guess<S>(d, wu, wl, xs);
+  for (int j = 0; j < S::QN; ++j) x[j] = xs[j];
+  return certified ? 1 : 0;
 }
 extern "C" int host_qps(const double* Ad, const double* lbd, const double* ubd, const double* lbu,
                         const double* ubu, const double* s, double* x, unsigned* au, unsigned* al, int max_iter,
@@ -201,7 +204,10 @@ def host_qps(tmp_path_factory):
         arrs = [A[DENSE_ROWS], lb[DENSE_ROWS], ub[DENSE_ROWS], lb[ur], ub[ur], 1.0 / np.sqrt(h)]
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
         wu, wl = ctypes.c_uint(seed[0]), ctypes.c_uint(seed[1])
-        lib.host_crash(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs], ctypes.byref(wu), ctypes.byref(wl))
+        x = np.zeros(6)
+        crash.certified = bool(lib.host_crash(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs], ctypes.byref(wu),
+                                              ctypes.byref(wl), x.ctypes.data_as(ctypes.c_void_p)))
+        crash.x = x
         return wu.value, wl.value
     solve.crash = crash
     return solve
@@ -300,12 +306,20 @@ def test_crash_start_guess_is_sound_and_never_changes_the_answer(host_qps):
     per column; started from it the solver returns the cold-start answer and flags; and for most
     problems it already IS the final working set."""
     rng = np.random.default_rng(33)
-    n_guess, n_ok, n_exact = 0, 0, 0
+    n_guess, n_ok, n_exact, n_cert = 0, 0, 0, 0
     for trial in range(400):
         h, A, lb, ub = _structured_problem(rng, eq_prob=3.0 if trial % 2 else 0.3, tight=(trial % 3 == 0))
         x, st, au, al = host_qps(h, A, lb, ub)
         wu, wl = host_qps.crash(h, A, lb, ub)
+        certified, xc = host_qps.crash.certified, host_qps.crash.x.copy()
         assert wu & wl == 0
+        if certified:
+            # a prediction that certifies itself IS the answer (the kernels return it without iterating)
+            assert st == 0 and (wu, wl) == (au, al), trial
+            assert np.abs(xc - x).max() < 1e-9 * (1 + np.abs(x).max()), trial
+            kk = orc.kkt_residuals(h, A, lb, ub, xc)
+            assert kk["primal"] < 1e-9 and kk["stationarity"] < 1e-9 and kk["sign"] < 1e-9, (trial, kk)
+            n_cert += 1
         for r in DENSE_ROWS:
             assert (wu | wl) >> r & 1 or lb[r] != ub[r]                   # every equality row is held
         cols = [c for r, c, k in UNIT if (wu | wl) >> r & 1]
@@ -330,4 +344,4 @@ def test_crash_start_guess_is_sound_and_never_changes_the_answer(host_qps):
         xs, sts, aus, als = host_qps(h, A, lb, ub, warm=(su, sl))
         if sts == 0:
             assert np.abs(xs - x).max() < 1e-9 * (1 + np.abs(x).max()) and (aus, als) == (au, al), trial
-    assert n_ok > 0.95 * n_guess and n_exact > 0.8 * n_guess, (n_guess, n_ok, n_exact)
+    assert n_ok > 0.95 * n_guess and n_exact > 0.8 * n_guess and n_cert > 0.8 * n_guess, (n_guess, n_ok, n_exact, n_cert)
