@@ -85,7 +85,11 @@ class ClockSampler(threading.Thread):
 def _launch_info(ctrl, is_qp):
     sk = ctrl._skill()
     if is_qp:
-        return sk.launch_info(1)
+        info = sk.launch_info(1)
+        if ctrl.kernel_meta.get("qp_split") and os.environ.get("CLIK_QP_SPLIT", "1") != "0":
+            info = {"fast": sk.launch_info(3), "tail": sk.launch_info(4), "full (status == NULL)": info,
+                    "used": "fast + tail"}
+        return info
     info = {"plain": sk.launch_info(0)}
     try:
         info["tma"] = sk.launch_info(2)
@@ -377,7 +381,8 @@ def main():
                             "kernel reads inputs from / writes results to mapped host memory over PCIe "
                             "inside the timed region (pageable buffers would take the chunked H2D / "
                             "kernel / D2H pipeline instead)"},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * (2 if (is_qp and meta.get("qp_split")
+                                                and os.environ.get("CLIK_QP_SPLIT", "1") != "0") else 1),
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and scenario.name == "ur5_track":

@@ -504,6 +504,8 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
                        ("true" if os.environ.get("CLIK_QP_CRASH", "1") == "1" else "false"))
             out.append("  static constexpr bool QP_CRASH_FINAL = %s;   // a certified prediction is returned as is" %
                        ("true" if os.environ.get("CLIK_QP_CRASH_FINAL", "1") == "1" else "false"))
+            crash_final = os.environ.get("CLIK_QP_CRASH_FINAL", "1") == "1" and os.environ.get("CLIK_QP_CRASH", "1") == "1"
+            meta["qp_split"] = crash_final and os.environ.get("CLIK_QP_SPLIT", "1") == "1"
             out.append("  static constexpr bool QP_EQ_START = %s;" %
                        ("true" if os.environ.get("CLIK_QP_EQ_START", "0") == "1" else "false"))
             out.append(_switch("dense_row", qp.dense_rows or [0]))
@@ -576,8 +578,22 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
         out.append("    const double* y, const double* x0, const unsigned* active0, double* sol, int* status,")
         out.append("    unsigned* active, int max_iter) {")
-        out.append("  clik::qp_step<Skill>(N, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
+        out.append("  clik::qp_step<Skill, clik::QP_FULL>(N, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
         out.append("}")
+        if meta.get("qp_split"):
+            # fast pass (working-set prediction only) + tail pass (full solver on what it left pending)
+            out.append('extern "C" __global__ void __launch_bounds__(%d) clik_qp_fast_kernel(' % block_threads)
+            out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
+            out.append("    const double* y, const double* x0, const unsigned* active0, double* sol, int* status,")
+            out.append("    unsigned* active, int max_iter) {")
+            out.append("  clik::qp_step<Skill, clik::QP_FAST>(N, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
+            out.append("}")
+            out.append('extern "C" __global__ void %s clik_qp_tail_kernel(' % qbounds)
+            out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
+            out.append("    const double* y, const double* x0, const unsigned* active0, double* sol, int* status,")
+            out.append("    unsigned* active, int max_iter) {")
+            out.append("  clik::qp_step_tail<Skill>(N, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
+            out.append("}")
     if qp is not None:
         out.append('extern "C" __global__ void __launch_bounds__(%d) clik_qp_rollout_kernel(' % block_threads)
         out.append("    long long N, int steps, double dt, const double* t0, int t_stride, double* q, double* x,")
@@ -590,8 +606,8 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
     if pinv is not None:
         flags |= 2 | (1 if os.environ.get("CLIK_TMA", "0") == "1" else 0)
     if qp is not None:
-        flags |= 4
-    out.append("  // manifest: sizes, unroll, optional-kernel flags (1 pinv TMA, 2 pinv rollout, 4 QP rollout)")
+        flags |= 4 | (16 if meta.get("qp_split") else 0)
+    out.append("  // manifest: sizes, unroll, optional-kernel flags (1 pinv TMA, 2 pinv rollout, 4 QP rollout, 16 QP fast + tail pair)")
     out.append("  o[0] = %d; o[1] = %d; o[2] = %d; o[3] = %d; o[4] = %d; o[5] = %d; o[6] = %d; o[7] = %d;"
                % (nq, nxv, ny, meta["n_modes"], meta["qp_n"], meta["qp_m"], meta.get("pinv_unroll", 1), flags))
     full = (1, 0xffffffff, 0xffffffff, 0xffffffff)

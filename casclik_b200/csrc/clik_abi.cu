@@ -71,7 +71,8 @@ struct ReadMask {
 struct clik_skill {
   clik_skill_desc desc;
   cudaLibrary_t lib = nullptr;
-  KernelInfo pinv, pinv_tma, pinv_rollout, qp, qp_rollout;
+  KernelInfo pinv, pinv_tma, pinv_rollout, qp, qp_fast, qp_tail, qp_rollout;
+  bool qp_split = true;  // CLIK_QP_SPLIT=0: always the single full kernel
   ReadMask pinv_reads, qp_reads;
   bool use_tma = false;  // opt-in (CLIK_TMA=1): measured slower than the plain kernel, see DESIGN.md
   int sm_count = 0;
@@ -369,6 +370,9 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
   if (st == CLIK_OK && desc->has_qp) {
     s->qp_reads = ReadMask{(unsigned)hsz[12], (unsigned)hsz[13], (unsigned)hsz[14], (unsigned)hsz[15]};
     if (flags & 4) st = setup_kernel(s, "clik_qp_rollout_kernel", &s->qp_rollout);
+    if (st == CLIK_OK && (flags & 16)) st = setup_kernel(s, "clik_qp_fast_kernel", &s->qp_fast);
+    if (st == CLIK_OK && (flags & 16)) st = setup_kernel(s, "clik_qp_tail_kernel", &s->qp_tail);
+    if (const char* e = getenv("CLIK_QP_SPLIT")) s->qp_split = atoi(e) != 0;
   }
   if (st != CLIK_OK) {
     cudaLibraryUnload(s->lib);
@@ -393,7 +397,7 @@ void clik_skill_free(clik_skill* s) {
 clik_status clik_skill_launch_info(const clik_skill* s, int32_t which, int32_t* grid, int32_t* block,
                                    int32_t* regs, int32_t* local_bytes) {
   if (!s) return fail(CLIK_ERR_INVALID, "skill is NULL");
-  const KernelInfo& k = which == 0 ? s->pinv : (which == 2 ? s->pinv_tma : s->qp);
+  const KernelInfo& k = which == 0 ? s->pinv : which == 2 ? s->pinv_tma : which == 3 ? s->qp_fast : which == 4 ? s->qp_tail : s->qp;
   if (!k.kernel) return fail(CLIK_ERR_INVALID, "skill has no such kernel");
   if (grid) *grid = k.grid;
   if (block) *block = k.block;
@@ -458,6 +462,17 @@ clik_status clik_qp_step(const clik_skill* s, int64_t N, const double* t, int32_
   int ts = t_stride ? 1 : 0;
   int mi = max_iter > 0 ? max_iter : 10 * (s->desc.qp_n + s->desc.qp_m);
   void* args[] = {&n, &t, &ts, &q, &x, &y, &x0, &active0, &sol, &status, &active, &mi};
+  if (s->qp_fast.kernel && s->qp_tail.kernel && s->qp_split && status != nullptr) {
+    // two launches: the working-set prediction for every instance (no Goldfarb-Idnani code in that
+    // kernel: ~160 registers instead of 255 + spills), then the full solver for the few instances the
+    // prediction could not certify; they are handed over through status[] (transient value 3).
+    CK(cudaLaunchKernel((const void*)s->qp_fast.kernel, dim3(grid_for(s->qp_fast, N)), dim3(s->qp_fast.block),
+                        args, 0, (cudaStream_t)stream));
+    const int64_t tiles = (N + clik::QP_TAIL_TILE - 1) / clik::QP_TAIL_TILE;
+    CK(cudaLaunchKernel((const void*)s->qp_tail.kernel, dim3((unsigned)std::min<int64_t>(tiles, 1 << 20)),
+                        dim3(s->qp_tail.block), args, 0, (cudaStream_t)stream));
+    return CLIK_OK;
+  }
   CK(cudaLaunchKernel((const void*)s->qp.kernel, dim3(grid_for(s->qp, N)), dim3(s->qp.block), args,
                       0, (cudaStream_t)stream));
   return CLIK_OK;

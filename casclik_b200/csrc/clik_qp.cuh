@@ -27,7 +27,7 @@
 
 namespace clik {
 
-enum : int { QP_OK = 0, QP_MAXITER = 1, QP_INFEASIBLE = 2 };
+enum : int { QP_OK = 0, QP_MAXITER = 1, QP_INFEASIBLE = 2, QP_PENDING = 3 /* transient: between the fast and the tail pass */ };
 
 // NXM / MM: compile-time capacities; nx / m: actual sizes (compile-time constants when inlined
 // into a fused skill kernel).  A is row-major m x nx and is overwritten with the scaled rows.
@@ -601,9 +601,9 @@ __device__ __forceinline__ void masks_from_x0(const QpSData<S>& D, const double 
 // row: joint position and joint speed limits bound the same column) — many rows change per pass, every
 // thread does the same work, and the set is final when it stops changing (for that problem: 83 % of the
 // instances after 3 passes, 99.4 % after 6).  Passes run until no thread of the warp changes its set
-// (at most CRASH_PASSES).  qp_structured then starts from the guess, repairs whatever is left and
+// (at most CRASH_PASSES; UR5 problem: 0.04 % of the instances are not final after 8 passes, 0.005 % after 12).  qp_structured then starts from the guess, repairs whatever is left and
 // certifies the result, so the answer never depends on it.
-constexpr int CRASH_PASSES = 8;
+constexpr int CRASH_PASSES = 12;
 template <class S>
 __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*in: guess, out*/,
                                             unsigned* lo, double (&xout)[S::QN]) {
@@ -788,78 +788,138 @@ template <class S> struct QpData {
   double h[S::QN];
 };
 
-// Fused step: evaluate the skill's QP matrices and solve, SoA in / SoA out.
-// sol[j*N + i] is entry j of x for instance i; active[i] = upper mask, active[N + i] = lower mask.
-template <class S>
-__device__ __forceinline__ void qp_step(long long N, const double* __restrict__ t, int t_stride,
-                                        const double* __restrict__ q, const double* __restrict__ x,
-                                        const double* __restrict__ y, const double* __restrict__ x0,
-                                        const unsigned* active0, double* __restrict__ sol,
-                                        int* __restrict__ status, unsigned* active, int max_iter) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-    double qv[S::NQ > 0 ? S::NQ : 1], xv[S::NX > 0 ? S::NX : 1], yv[S::NY > 0 ? S::NY : 1];
-    const double tv = __ldcs(t + (long long)t_stride * i);
+// One instance of the fused step: load, evaluate the skill's QP matrices, solve, store.
+// MODE QP_FAST: only the working-set prediction runs; an instance it cannot certify is marked
+// QP_PENDING in status[i], its uncertified prediction is parked in active[] (if present), nothing else
+// is written.  MODE QP_TAIL: the full solver for such an instance, started from the parked prediction.
+enum : int { QP_FULL = 0, QP_FAST = 1, QP_TAIL = 2 };
+template <class S, int MODE>
+__device__ __forceinline__ void qp_instance(long long N, long long i, const double* __restrict__ t, int t_stride,
+                                            const double* __restrict__ q, const double* __restrict__ x,
+                                            const double* __restrict__ y, const double* __restrict__ x0,
+                                            const unsigned* active0, double* __restrict__ sol,
+                                            int* __restrict__ status, unsigned* active, int max_iter) {
+  double qv[S::NQ > 0 ? S::NQ : 1], xv[S::NX > 0 ? S::NX : 1], yv[S::NY > 0 ? S::NY : 1];
+  const double tv = __ldcs(t + (long long)t_stride * i);
 #pragma unroll
-    for (int j = 0; j < S::NQ; ++j) qv[j] = __ldcs(q + (long long)j * N + i);
+  for (int j = 0; j < S::NQ; ++j) qv[j] = __ldcs(q + (long long)j * N + i);
 #pragma unroll
-    for (int j = 0; j < S::NX; ++j) xv[j] = __ldcs(x + (long long)j * N + i);
+  for (int j = 0; j < S::NX; ++j) xv[j] = __ldcs(x + (long long)j * N + i);
 #pragma unroll
-    for (int j = 0; j < S::NY; ++j) yv[j] = __ldcs(y + (long long)j * N + i);
-    double xs[S::QN];
-    unsigned mu, ml;
-    int st;
-    if constexpr (S::QSTRUCT) {
-      QpSData<S> d;
-      S::eval_qps(tv, qv, xv, yv, d);
-      // warm start: an explicit working-set guess (active0, may alias `active`) wins over one
-      // derived from the primal guess x0; neither changes the answer, only the iteration count
-      unsigned wu = 0u, wl = 0u;
-      if (active0 != nullptr) {
-        wu = active0[i];
-        wl = active0[N + i];
-      } else if (x0 != nullptr) {
-        double x0v[S::QN];
+  for (int j = 0; j < S::NY; ++j) yv[j] = __ldcs(y + (long long)j * N + i);
+  double xs[S::QN];
+  unsigned mu, ml;
+  int st;
+  if constexpr (S::QSTRUCT) {
+    QpSData<S> d;
+    S::eval_qps(tv, qv, xv, yv, d);
+    // warm start: an explicit working-set guess (active0, may alias `active`) wins over one
+    // derived from the primal guess x0; neither changes the answer, only the iteration count
+    unsigned wu = 0u, wl = 0u;
+    const bool parked = MODE == QP_TAIL && active != nullptr;
+    if (parked) {
+      wu = active[i];
+      wl = active[N + i];
+    } else if (active0 != nullptr) {
+      wu = active0[i];
+      wl = active0[N + i];
+    } else if (x0 != nullptr) {
+      double x0v[S::QN];
 #pragma unroll
-        for (int j = 0; j < S::QN; ++j) x0v[j] = x0[(long long)j * N + i];
-        masks_from_x0<S>(d, x0v, &wu, &wl);
-      } else if (!S::QP_CRASH && S::QP_EQ_START) {
-        // no guess: equality rows are active at every solution, start with them held
+      for (int j = 0; j < S::QN; ++j) x0v[j] = x0[(long long)j * N + i];
+      masks_from_x0<S>(d, x0v, &wu, &wl);
+    } else if (!S::QP_CRASH && S::QP_EQ_START) {
+      // no guess: equality rows are active at every solution, start with them held
 #pragma unroll
-        for (int a = 0; a < S::QMD; ++a) {
-          if (S::dense_row(a) < 32 && d.lbd[a] == d.ubd[a]) wu |= 1u << S::dense_row(a);
-        }
+      for (int a = 0; a < S::QMD; ++a) {
+        if (S::dense_row(a) < 32 && d.lbd[a] == d.ubd[a]) wu |= 1u << S::dense_row(a);
       }
-      // predicts the working set from any guess, or none; when the prediction certifies itself its
-      // face optimum is the answer and the iteration below is skipped
-      bool solved = false;
-      if (S::QP_CRASH) solved = crash_guess<S>(d, &wu, &wl, xs) && S::QP_CRASH_FINAL;
-      st = solved ? QP_OK : QP_MAXITER;
-      mu = wu;
-      ml = wl;
+    }
+    // predicts the working set from any guess, or none; when the prediction certifies itself its
+    // face optimum is the answer and the iteration below is skipped
+    bool solved = false;
+    if (S::QP_CRASH && !parked) solved = crash_guess<S>(d, &wu, &wl, xs) && S::QP_CRASH_FINAL;
+    st = solved ? QP_OK : QP_MAXITER;
+    mu = wu;
+    ml = wl;
+    if constexpr (MODE == QP_FAST) {
+      if (!solved) {
+        status[i] = QP_PENDING;
+        if (active != nullptr) {
+          active[i] = wu;
+          active[N + i] = wl;
+        }
+        return;
+      }
+    } else {
 #pragma unroll 1
       for (int attempt = 0; attempt < 2 && !solved; ++attempt) {   // a bad guess must never cost the answer:
-        if (attempt > 0) {                              // second attempt = cold start
+        if (attempt > 0) {                                         // second attempt = cold start
           wu = wl = 0u;
           S::eval_qps(tv, qv, xv, yv, d);
         }
         st = qp_structured<S>(d, xs, &mu, &ml, max_iter, wu, wl);
         if (st == QP_OK || (wu | wl) == 0u) break;
       }
-    } else {
-      QpData<S> d;
-      S::eval_qp(tv, qv, xv, yv, d);
-      st = qp_dual_active_set<S::QN, S::QM>(S::QN, S::QM, d.A, d.lb, d.ub, d.h, nullptr, xs, &mu, &ml,
-                                            max_iter);
     }
-    for (int j = 0; j < S::QN; ++j) __stcs(sol + (long long)j * N + i, xs[j]);
-    if (status != nullptr) status[i] = st;
-    if (active != nullptr) {
-      active[i] = mu;
-      active[N + i] = ml;
-    }
+  } else {
+    QpData<S> d;
+    S::eval_qp(tv, qv, xv, yv, d);
+    st = qp_dual_active_set<S::QN, S::QM>(S::QN, S::QM, d.A, d.lb, d.ub, d.h, nullptr, xs, &mu, &ml,
+                                          max_iter);
+  }
+  for (int j = 0; j < S::QN; ++j) __stcs(sol + (long long)j * N + i, xs[j]);
+  if (status != nullptr) status[i] = st;
+  if (active != nullptr) {
+    active[i] = mu;
+    active[N + i] = ml;
   }
 }
+
+// Fused step, SoA in / SoA out: sol[j*N + i] is entry j of x for instance i; active[i] = upper mask,
+// active[N + i] = lower mask.  One kernel does everything (MODE = QP_FULL), or — structured skills with
+// the working-set prediction, status array present — a QP_FAST pass followed by qp_step_tail.  The split
+// keeps the Goldfarb-Idnani iteration (255 registers + spills, needed by well under 1 % of the
+// instances) out of the kernel every instance runs (159 registers for the UR5 problem).
+template <class S, int MODE>
+__device__ __forceinline__ void qp_step(long long N, const double* __restrict__ t, int t_stride,
+                                        const double* __restrict__ q, const double* __restrict__ x,
+                                        const double* __restrict__ y, const double* __restrict__ x0,
+                                        const unsigned* active0, double* __restrict__ sol,
+                                        int* __restrict__ status, unsigned* active, int max_iter) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
+    qp_instance<S, MODE>(N, i, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);
+}
+
+// Tail pass: every CTA scans QP_TAIL_TILE consecutive status entries, collects the instances the FAST
+// pass left QP_PENDING into shared memory and solves those with the full path, densely packed into
+// its first threads (no global scratch, so calls on different streams do not interfere).
+constexpr int QP_TAIL_TILE = 1024;
+#ifdef __CUDACC__   // (the host-compiled test harness of the solvers has no shared memory)
+template <class S>
+__device__ __forceinline__ void qp_step_tail(long long N, const double* __restrict__ t, int t_stride,
+                                             const double* __restrict__ q, const double* __restrict__ x,
+                                             const double* __restrict__ y, const double* __restrict__ x0,
+                                             const unsigned* active0, double* __restrict__ sol,
+                                             int* __restrict__ status, unsigned* active, int max_iter) {
+  __shared__ int list[QP_TAIL_TILE];
+  __shared__ int count;
+  for (long long base = (long long)blockIdx.x * QP_TAIL_TILE; base < N; base += (long long)gridDim.x * QP_TAIL_TILE) {
+    if (threadIdx.x == 0) count = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < QP_TAIL_TILE && base + k < N; k += blockDim.x) {
+      if (status[base + k] == QP_PENDING) list[atomicAdd(&count, 1)] = k;
+    }
+    __syncthreads();
+    const int n = count;
+    for (int k = threadIdx.x; k < n; k += blockDim.x)
+      qp_instance<S, QP_TAIL>(N, base + list[k], t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);
+    __syncthreads();
+  }
+}
+
+#endif
 
 // Closed-loop rollout with the QP controller: `steps` times  sol = solve(t0 + k*dt, q, x, y);
 // v = clip(sol[:n], +-max_speed); q += v_rob*dt; x += v_virt*dt  (the notebooks' simulation loop,

@@ -102,7 +102,10 @@ clik_status clik_pinv_rollout(const clik_skill* skill, int64_t N, int32_t steps,
  *   active0 [2 * N] or NULL: explicit working-set guess in the format of `active` (e.g. the
  *          previous step's output; may alias `active`); takes precedence over x0
  *   sol    [qp_n * N] out: [robot vel; virtual vel; slack]
- *   status [N] out, may be NULL: CLIK_QP_*
+ *   status [N] out, may be NULL: CLIK_QP_*.  With a status array, skills built with the working-set
+ *          prediction run as two launches (prediction for every instance, then the full solver on the
+ *          instances it could not certify, handed over through status[] with the transient value 3);
+ *          with status == NULL, or CLIK_QP_SPLIT=0 in the environment, as one launch.  Same results.
  *   active [2 * N] out, may be NULL: active[i] bit r = row r at its upper bound,
  *          active[N + i] bit r = row r at its lower bound (rows >= 32 are not reported)
  *   max_iter <= 0 selects the default cap 10 * (qp_n + qp_m). */
@@ -141,7 +144,7 @@ clik_status clik_qp_step_host(const clik_skill* skill, int64_t N, const double* 
                               int32_t max_iter);
 
 /* Launch geometry chosen at load time (for reporting). */
-clik_status clik_skill_launch_info(const clik_skill* skill, int32_t which /*0 pinv, 1 qp, 2 pinv TMA-staged*/,
+clik_status clik_skill_launch_info(const clik_skill* skill, int32_t which /*0 pinv, 1 qp, 2 pinv TMA-staged, 3 qp fast pass, 4 qp tail pass*/,
                                    int32_t* grid, int32_t* block, int32_t* regs_per_thread,
                                    int32_t* local_bytes_per_thread);
 

@@ -272,3 +272,29 @@ def test_kitchen_sink_qp_parity():
         assert kk["primal"] < 1e-8 and kk["stationarity"] < 1e-8 and kk["sign"] < 1e-8
         up_o, lo_o = _masks(lamo[None, :])
         assert active[0, i] == up_o[0] and active[1, i] == lo_o[0]
+
+
+def test_two_launch_split_equals_the_single_kernel(monkeypatch):
+    """clik_qp_step with a status array runs the working-set prediction and the full solver as two
+    launches (handing over through status[]); CLIK_QP_SPLIT=0 keeps everything in one kernel.  Same
+    bits, for cold, x0-warm and active-set-warm calls, on ragged sizes that leave partial tiles."""
+    torch = _torch()
+    sc = scenarios.get("ur5_qp")
+    N = 5000 + 37
+    inp = sc.sample(N, seed=9)
+    dev = {k: (None if v is None else torch.from_numpy(np.ascontiguousarray(v)).cuda()) for k, v in inp.items()}
+    outs = {}
+    for split in ("1", "0"):
+        monkeypatch.setenv("CLIK_QP_SPLIT", split)
+        ctrl = sc.make_controller()
+        ctrl.setup_problem_functions()
+        ctrl.setup_solver()
+        assert bool(ctrl.kernel_meta.get("qp_split")) == (split == "1")
+        cold = ctrl.solve_batch(dev["t"], dev["q"], None, dev["y"])
+        warm_x = ctrl.solve_batch(dev["t"], dev["q"], None, dev["y"], warmstart=cold[0])
+        warm_a = ctrl.solve_batch(dev["t"], dev["q"], None, dev["y"], warm_active=cold[2])
+        outs[split] = [tuple(t.clone() for t in r) for r in (cold, warm_x, warm_a)]
+    for a, b in zip(outs["1"], outs["0"]):
+        for ta, tb in zip(a, b):
+            assert torch.equal(ta, tb)
+    assert int(outs["1"][0][1].abs().sum()) == 0          # every status final (0), none left pending
