@@ -219,6 +219,41 @@ def kitchen_sink_qp(ns, rng, N):
     return spec, inp
 
 
+def _cart_points(rng, N):
+    p = rng.uniform(-0.3, 1.4, N)
+    p[:6] = [0.25, 1.2, 0.0, 1.0, 0.6, -0.1]          # the known-answer points of SURVEY §8c first
+    return {"t": np.zeros(N), "q": p.reshape(1, N)}
+
+
+def cart_pinv(ns, rng, N, target=0.75):
+    """cart_on_track notebook, pinv flavour (SURVEY §8c KATs P1-P3)."""
+    cs = ns.cs
+    t, p, dp = cs.MX.sym("t"), cs.MX.sym("p"), cs.MX.sym("dp")
+    lim = ns.SetConstraint("cart_limit_cnstr", p, gain=1.0, set_min=0.0, set_max=1.0, priority=1)
+    eq = ns.EqualityConstraint("min_dist_cnstr", target - p, gain=1.0, priority=2)
+    spec = ns.SkillSpecification("cart", t, p, robot_vel_var=dp, constraints=[eq, lim])
+    return spec, _cart_points(rng, N)
+
+
+def cart_pinv_far(ns, rng, N):
+    return cart_pinv(ns, rng, N, target=1.5)
+
+
+def cart_qp(ns, rng, N):
+    """cart_on_track notebook, QP flavour (SURVEY §8c KATs Q1-Q2)."""
+    cs = ns.cs
+    t, p, dp = cs.MX.sym("t"), cs.MX.sym("p"), cs.MX.sym("dp")
+    eq = ns.EqualityConstraint("min_dist_cnstr", 0.75 - p, gain=1.0, constraint_type="soft", priority=1)
+    lim = ns.SetConstraint("cart_limit_cnstr", p, gain=1.0, set_min=0.0, set_max=1.0)
+    spd = ns.VelocitySetConstraint("speed_limit_cnstr", p, gain=10.0, set_min=-0.275, set_max=0.275)
+    spec = ns.SkillSpecification("cart_qp", t, p, robot_vel_var=dp, constraints=[eq, lim, spd])
+    inp = _cart_points(rng, N)
+    # further than 0.275 outside [0, 1] the hard limit row and the hard speed row contradict each other
+    # (the reference raises there; casclik_b200 reports status 2 — tests/test_gpu_qp.py)
+    inp["q"] = np.clip(inp["q"], -0.25, 1.25)
+    return spec, inp
+
+
 # name -> (builder, controller, constructor keyword arguments)
 CASES = {
     "pinv/ur5_track": (ur5_track, "pinv", {}),
@@ -233,6 +268,9 @@ CASES = {
     "pinv/kitchen_sink": (kitchen_sink, "pinv", {}),
     "pinv/kitchen_sink_damping_1e-4": (kitchen_sink, "pinv", {"options": {"damping_factor": 1e-4}}),
     "pinv/conv_last": (conv_last, "pinv", {"options": {"converge_final_set_to_max": True}}),
+    "pinv/cart_kat": (cart_pinv, "pinv", {}),
+    "pinv/cart_kat_far_target": (cart_pinv_far, "pinv", {}),
+    "qp/cart_kat": (cart_qp, "qp", {"robot_var_weights": [1.0]}),
     "qp/ur5_qp": (ur5_qp, "qp", {}),
     "qp/ur5_moe2016": (ur5_moe2016, "qp", {}),
     "qp/cart_path": (cart_path_qp, "qp", {"robot_var_weights": [1.0]}),
@@ -242,7 +280,8 @@ CASES = {
 
 
 def seed_of(name):
-    return 1000 + sorted(CASES).index(name)
+    import zlib
+    return zlib.crc32(name.encode()) % (1 << 31)       # stable when cases are added
 
 
 def build(ns, name, inputs=None, N=N_CANDIDATES):

