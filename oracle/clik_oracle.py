@@ -10,7 +10,7 @@ The oracle is pinned against outputs of the reference's OWN controller code run 
 container: tests/golden/make_controller_vectors.py imports the unmodified /root/reference/casclik
 package with a stand-in `casadi` module (casclik_b200.sym evaluated by NumPy; `conic` -> this file's
 QP solver on the reference-built H, A, lba, uba) and drives PseudoInverseController.solve /
-ReactiveQPController.solve one instance at a time on 16 skill/option cases ->
+ReactiveQPController.solve one instance at a time on 19 skill/option cases ->
 tests/golden/controller_vectors.json (modes, velocities, QP matrices and minimisers;
 tests/test_golden_controllers.py: modes bit-exact, velocities to ~1e-12).  What that does NOT pin is
 CasADi's and qpOASES' own floating-point arithmetic (they would differ from the stand-in at rounding
