@@ -56,3 +56,20 @@ def test_no_cpu_fallback_without_a_device():
         ctrl.solve(0.0, [0.1] * 6, input_var=[0.3, 0.3, 0.3])
     with pytest.raises(runtime.ClikError):
         ctrl.setup_solver()
+
+
+def test_product_tree_never_touches_the_oracle_or_the_reference():
+    """oracle/ is test infrastructure and /root/reference does not exist on the GPU box: nothing under
+    casclik_b200/ (Python, CUDA, headers) may import, include, link or open either."""
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "casclik_b200")
+    bad = []
+    for dirpath, dirnames, filenames in os.walk(root):
+        dirnames[:] = [d for d in dirnames if d not in ("_cache", "__pycache__")]
+        for fn in filenames:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, fn), encoding="utf-8", errors="replace").read()
+                if re.search(r"clik_oracle|oracle[/\\.]|/root/reference", text) or \
+                        re.search(r"^\s*(import|from)\s+casadi\b", text, re.M):
+                    bad.append(os.path.join(dirpath, fn))
+    assert bad == []
