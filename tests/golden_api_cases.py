@@ -135,6 +135,7 @@ CASES = {
     "qp/list_weights": lambda ns: _qp(ns, robot_var_weights=[1.0, 2.0, 3.0], virtual_var_weights=[4.0],
                                       slack_var_weights=[1.0, 2.0, 3.0]),
     "qp/array_weights": lambda ns: _qp(ns, robot_var_weights=np.array([0.5, 0.5, 2.0])),
+    "qp/dm_weights": lambda ns: _qp(ns, robot_var_weights=ns.cs.DM([1.0, 2.0, 3.0])),
     "qp/robot_weights_wrong_length": lambda ns: _qp(ns, robot_var_weights=[1.0, 2.0]),
     "qp/virtual_weights_wrong_length": lambda ns: _qp(ns, virtual_var_weights=[1.0, 2.0]),
     "qp/slack_weights_wrong_length": lambda ns: _qp(ns, slack_var_weights=[1.0]),

@@ -20,6 +20,10 @@ DEVIATIONS = {
     # an (n, 1) numpy column as set_max: the reference's size check compares the wrong variable
     # (`szi == 1`, constraints.py:262) and rejects what it accepts for set_min two branches earlier
     "set/column_array_bounds": {"ok": [[-1.0, -2.0], [1.0, 2.0], 1, "hard"]},
+    # DM / MX weights: the reference's setters compare the bound method `weights.size2` with 1
+    # (reactive_qp.py:69-74) and so reject every CasADi-typed weight vector
+    "qp/dm_weights": {"ok": {"H_diag": [0.001, 0.002, 0.003, 0.001, 2.501, 2.501, 1.001], "H_offdiag_nnz": 0,
+                             "mu": 0.001, "solver": "qpoases"}},
 }
 
 
