@@ -4,6 +4,7 @@ import os
 from . import converter  # noqa: F401
 from .converter import from_file, from_denavit_hartenberg, parse_urdf, chain  # noqa: F401
 from . import pose_errors  # noqa: F401
+from . import casadi_geom, numpy_geom  # noqa: F401  (urdf2casadi.casadi_geom / numpy_geom stand-ins)
 
 ROBOT_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "robots")
 UR5_URDF = os.path.join(ROBOT_DIR, "ur5_chain.urdf")

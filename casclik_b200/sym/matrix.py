@@ -183,6 +183,11 @@ class GenericMatrixCommon(object):
     def __array__(self, dtype=None, copy=None):
         if self.is_constant():
             out = self.toarray()
+            if out.shape == (1, 1):
+                # a numeric scalar acts as a 0-d array, so that NumPy accepts it as an element:
+                # `y_sim[i, :] = [fcos(t), fsine(t), 0]` with DM-valued Function results
+                # (ur5_input_experiment.ipynb cell 16).  toarray() / full() stay 2-D.
+                out = out.reshape(())
             return out if dtype is None else out.astype(dtype)
         return self._a
 

@@ -110,3 +110,52 @@ def test_pose_error_forms_of_the_notebooks():
     lhs = pe.dual_quaternion_product(A, B).toarray()[:, 0]
     rhs = (pe.dual_hamilton_operator_minus(B).toarray() @ A)
     assert np.abs(lhs - rhs).max() < 1e-14 and abs(np.linalg.norm(A[:4]) - 1.0) < 1e-14
+
+
+def test_geometry_helper_modules_of_the_notebooks():
+    """fk.casadi_geom / fk.numpy_geom stand in for urdf2casadi.casadi_geom / numpy_geom as the
+    dual-quaternion notebooks use them (wrapped in cs.Functions of SX symbols, desired frames,
+    identity dual quaternion); conventions are pinned by the FK itself: [x y z w | dual]."""
+    from casclik_b200.fk import casadi_geom as cg, numpy_geom as ng
+    d = fk.ur5()
+    rng = np.random.default_rng(3)
+    quat1, quat2 = cs.SX.sym("quat1", 8), cs.SX.sym("quat2", 8)
+    dq_prod = cs.Function("dualquatprod", [quat1, quat2], [cg.dual_quaternion_product(quat1, quat2)])
+    dq_conj = cs.Function("dualquatconj", [quat1], [cg.dual_quaternion_conj(quat1)])
+    dq_inv = cs.Function("dualquatinv", [quat1], [cg.dual_quaternion_inv(quat1)])
+    dq_T = cs.Function("dualquat2transfmat", [quat1], [cg.dual_quaternion_to_transformation_matrix(quat1)])
+    dq_pos = cs.Function("dualquat2pos", [quat1], [cg.dual_quaternion_to_pos(quat1)])
+    dq_norm = cs.Function("dualquatdualnorm", [quat1], [cg.dual_quaternion_norm2(quat1)[0],
+                                                         cg.dual_quaternion_norm2(quat1)[1]])
+    axis, ang = cs.SX.sym("axis", 3), cs.SX.sym("ang")
+    dq_rot = cs.Function("dualquataxisrot", [axis, ang], [cg.dual_quaternion_axis_rotation(axis, ang)])
+    dq_tr = cs.Function("dualquataxistransl", [axis, ang], [cg.dual_quaternion_axis_translation(axis, ang)])
+    identity = np.array([0, 0, 0, 1, 0, 0, 0, 0.0])
+    assert np.array_equal(ng.dual_quaternion_revolute([0., 0., 0.], [0., 0., 0.], [1., 0., 0.], 0.0), identity)
+    for _ in range(10):
+        q = rng.uniform(-3, 3, 6)
+        Q = d["dual_quaternion_fk"](q)
+        T = np.asarray(d["T_fk"](q).toarray())
+        assert np.abs(np.asarray(dq_T(Q).toarray()) - T).max() < 1e-13
+        assert np.abs(ng.dual_quaternion_to_transformation_matrix(Q.toarray()) - T).max() < 1e-13
+        assert np.abs(np.asarray(dq_pos(Q).toarray())[:, 0] - T[:3, 3]).max() < 1e-13
+        assert np.abs(np.asarray(dq_prod(Q, dq_conj(Q)).toarray())[:, 0] - identity).max() < 1e-13
+        assert np.abs(np.asarray(dq_prod(Q, dq_inv(Q)).toarray())[:, 0] - identity).max() < 1e-13
+        a, b = dq_norm(Q)
+        assert abs(float(a) - 1.0) < 1e-13 and abs(float(b)) < 1e-13
+        xyz, rpy = rng.uniform(-1, 1, 3), rng.uniform(-3, 3, 3)
+        ax = rng.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        th = rng.uniform(-3, 3)
+        # joint transform two ways: dual quaternions vs homogeneous matrices
+        Qj = ng.dual_quaternion_revolute(xyz, rpy, ax, th)
+        Rj = np.asarray(dq_T(dq_rot(ax, th)).toarray())
+        assert np.abs(ng.dual_quaternion_to_transformation_matrix(Qj) - ng.T_rpy(xyz, *rpy) @ Rj).max() < 1e-13
+        assert np.abs(np.asarray(cs.DM(cg.dual_quaternion_revolute(xyz, rpy, ax, th)).toarray())[:, 0] - Qj).max() < 1e-14
+        Qp = ng.dual_quaternion_prismatic(xyz, rpy, ax, 0.3)
+        Tp = ng.T_rpy(xyz, *rpy) @ np.asarray(dq_T(dq_tr(ax, 0.3)).toarray())
+        assert np.abs(ng.dual_quaternion_to_transformation_matrix(Qp) - Tp).max() < 1e-13
+        assert np.abs(ng.rotation_rpy(*rpy) - ng.T_rpy(xyz, *rpy)[:3, :3]).max() == 0.0
+        assert np.abs(np.asarray(cs.DM(cg.dual_quaternion_rpy(rpy)).toarray())[:, 0] - ng.dual_quaternion_rpy(rpy)).max() < 1e-15
+        assert np.abs(np.asarray(cs.DM(cg.dual_quaternion_translation(xyz)).toarray())[:, 0]
+                      - ng.dual_quaternion_translation(xyz)).max() == 0.0

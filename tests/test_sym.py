@@ -139,3 +139,16 @@ def test_dm_prints_like_casadi():
     assert str(cs.DM([1, 2, 3])) == "[1, 2, 3]"
     assert "Distance: " + str(cs.norm_2(cs.DM([3.0, 4.0]))) == "Distance: 5"
     assert str(cs.MX.sym("q", 2)).startswith("MX(2x1")
+
+
+def test_numeric_scalars_are_numpy_elements():
+    """DM-valued Function results inside a list assigned to a NumPy row
+    (`y_sim[i, :] = [fcos(t), fsine(t), 0]`, ur5_input_experiment.ipynb cell 16)."""
+    x = cs.MX.sym("x")
+    fcos = cs.Function("fcos", [x], [0.1 * cs.cos(x)])
+    y = np.zeros((2, 3))
+    y[1, :] = [fcos(0.0), fcos(np.pi), 0]
+    assert np.allclose(y[1], [0.1, -0.1, 0.0])
+    assert np.asarray(cs.DM(2.5)).shape == () and cs.DM(2.5).toarray().shape == (1, 1)
+    assert np.asarray(cs.DM([1.0, 2.0])).shape == (2, 1)
+    assert max(min(cs.DM(0.3), 0.2), -0.2) == 0.2          # clipping a DM command like the notebooks do
