@@ -19,7 +19,12 @@ sys.path.insert(0, ROOT)
 NB_DIR = "/root/reference/examples/notebooks"
 
 import casclik_b200 as cc  # noqa: E402
-from casclik_b200 import cs, fk  # noqa: E402
+from casclik_b200 import build as _build, cs, fk  # noqa: E402
+import tempfile  # noqa: E402
+
+# the ~60 controllers the notebooks define would otherwise land in the in-tree cubin cache that
+# travels to the GPU box
+_build.CACHE_DIR = tempfile.mkdtemp(prefix="clik_notebook_audit_")
 
 # --- module stand-ins ------------------------------------------------------------------------------
 sys.modules["casadi"] = cs
