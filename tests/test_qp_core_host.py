@@ -345,3 +345,113 @@ def test_crash_start_guess_is_sound_and_never_changes_the_answer(host_qps):
         if sts == 0:
             assert np.abs(xs - x).max() < 1e-9 * (1 + np.abs(x).max()) and (aus, als) == (au, al), trial
     assert n_ok > 0.95 * n_guess and n_exact > 0.8 * n_guess and n_cert > 0.8 * n_guess, (n_guess, n_ok, n_exact, n_cert)
+
+
+# ---- the structured solver + working-set prediction on other row structures -------------------------------
+SHIM_G = SHIM.split('#include "%s"')[0] + r'''
+#include <cstring>
+#include "%(hdr)s"
+struct S {
+  static constexpr int QN = %(qn)d, QMD = %(md)d, QMU = %(mu)d, QM = %(qm)d;
+  static constexpr int dense_row(int a) { constexpr int t[%(md1)d] = {%(dense)s}; return t[a]; }
+  static constexpr int unit_row(int i) { constexpr int t[%(mu1)d] = {%(urow)s}; return t[i]; }
+  static constexpr int unit_col(int i) { constexpr int t[%(mu1)d] = {%(ucol)s}; return t[i]; }
+  static constexpr double unit_coef(int i) { constexpr double t[%(mu1)d] = {%(ucoef)s}; return t[i]; }
+};
+static void fill(clik::QpSData<S>& d, const double* Ad, const double* lbd, const double* ubd, const double* lbu,
+                 const double* ubu, const double* s) {
+  std::memcpy(d.Ad, Ad, sizeof(double) * (S::QMD > 0 ? S::QMD : 1) * S::QN);
+  std::memcpy(d.lbd, lbd, sizeof(d.lbd)); std::memcpy(d.ubd, ubd, sizeof(d.ubd));
+  std::memcpy(d.lbu, lbu, sizeof(d.lbu)); std::memcpy(d.ubu, ubu, sizeof(d.ubu)); std::memcpy(d.s, s, sizeof(d.s));
+}
+// mode 0: cold Goldfarb-Idnani; 1: prediction, then (if not certified) the iteration from it -- what the kernels do
+extern "C" int solve(const double* Ad, const double* lbd, const double* ubd, const double* lbu, const double* ubu,
+                     const double* s, double* x, unsigned* au, unsigned* al, int mode, int* certified) {
+  clik::QpSData<S> d;
+  fill(d, Ad, lbd, ubd, lbu, ubu, s);
+  double xs[S::QN];
+  unsigned wu = 0, wl = 0;
+  int st;
+  *certified = 0;
+  if (mode == 1 && clik::crash_guess<S>(d, &wu, &wl, xs)) {
+    *certified = 1; st = 0; *au = wu; *al = wl;
+  } else {
+    st = clik::qp_structured<S>(d, xs, au, al, 400, wu, wl);
+    if (st != 0 && (wu | wl) != 0) { fill(d, Ad, lbd, ubd, lbu, ubu, s); st = clik::qp_structured<S>(d, xs, au, al, 400, 0u, 0u); }
+  }
+  for (int j = 0; j < S::QN; ++j) x[j] = xs[j];
+  return st;
+}
+'''
+
+STRUCTURES = {
+    # name: (nx, dense rows, [(unit row, column, coefficient)])
+    "ur5_like_3_dense_two_bounds_per_joint": (9, [0, 1, 2], [(3 + i, i % 6, 1.0) for i in range(12)]),
+    "six_dense_no_unit_rows": (9, [0, 1, 2, 3, 4, 5], []),
+    "unit_rows_only_mixed_signs": (5, [], [(0, 0, 1.0), (1, 1, -2.0), (2, 2, 0.5), (3, 0, -1.0), (4, 4, 3.0)]),
+    "four_dense_interleaved": (7, [1, 3, 4, 6], [(0, 0, 1.0), (2, 6, -1.0), (5, 3, 2.0), (7, 0, 1.0), (8, 5, 1.0)]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(STRUCTURES))
+def test_prediction_plus_iteration_equals_cold_solve_on_other_structures(name, tmp_path):
+    nx, dense, unit = STRUCTURES[name]
+    m = len(dense) + len(unit)
+    ints = lambda v: ", ".join(str(int(i)) for i in (v or [0]))  # noqa: E731
+    src = tmp_path / "s.cpp"
+    src.write_text(SHIM_G % dict(hdr=os.path.join(ROOT, "casclik_b200", "csrc", "clik_qp.cuh"), qn=nx, md=len(dense),
+                                 mu=len(unit), qm=m, md1=max(len(dense), 1), mu1=max(len(unit), 1), dense=ints(dense),
+                                 urow=ints([u[0] for u in unit]), ucol=ints([u[1] for u in unit]),
+                                 ucoef=", ".join(repr(float(u[2])) for u in unit) or "1.0"))
+    so = tmp_path / "s.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", str(so), str(src)], check=True)
+    lib = ctypes.CDLL(str(so))
+    urows = [u[0] for u in unit]
+    P = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+
+    def run(h, A, lb, ub, mode):
+        pad = lambda v: v if len(v) else np.zeros(1)  # noqa: E731
+        arrs = [np.ascontiguousarray(A[dense]) if dense else np.zeros(nx), pad(lb[dense]), pad(ub[dense]),
+                pad(lb[urows]), pad(ub[urows]), 1.0 / np.sqrt(h)]
+        keep = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
+        x = np.zeros(nx)
+        au, al, cert = ctypes.c_uint(), ctypes.c_uint(), ctypes.c_int()
+        st = lib.solve(*[P(a) for a in keep], P(x), ctypes.byref(au), ctypes.byref(al), mode, ctypes.byref(cert))
+        return x, st, au.value, al.value, cert.value
+
+    rng = np.random.default_rng(sum(map(ord, name)))
+    n_cert = n_ok = 0
+    for trial in range(250):
+        A = np.zeros((m, nx))
+        if dense:
+            A[dense] = rng.normal(size=(len(dense), nx))
+        for r, c, k in unit:
+            A[r, c] = k
+        h = rng.uniform(0.001, 2.0, nx)
+        r0 = A @ rng.normal(size=nx)
+        w = 0.05 if trial % 3 == 0 else 1.0
+        lb, ub = r0 - rng.uniform(0, w, m), r0 + rng.uniform(0, w, m)
+        for i in range(m):
+            u = rng.random()
+            if u < 0.08:
+                lb[i] = -np.inf
+            elif u < 0.16:
+                ub[i] = np.inf
+            elif u < 0.24:
+                lb[i], ub[i] = -1e10, 1e10
+            elif u < 0.40 and i in dense:
+                lb[i] = ub[i] = r0[i]
+        xo, lamo, sto = orc.solve_qp_single(h, A, lb, ub)
+        x0, st0, au0, al0, _ = run(h, A, lb, ub, 0)
+        x1, st1, au1, al1, cert = run(h, A, lb, ub, 1)
+        assert st0 == st1 == sto, (trial, st0, st1, sto)
+        if sto != 0:
+            continue
+        n_ok += 1
+        n_cert += cert
+        for x in (x0, x1):
+            assert np.abs(x - xo).max() < 1e-8 * (1 + np.abs(xo).max()), (trial, cert)
+            kk = orc.kkt_residuals(h, A, lb, ub, x)
+            assert kk["primal"] < 1e-8 and kk["stationarity"] < 1e-8 and kk["sign"] < 1e-8, (trial, cert, kk)
+        assert (au0, al0) == (au1, al1) == _masks(lamo), (trial, cert)
+    assert n_ok > 150 and n_cert > 0.6 * n_ok, (n_ok, n_cert)
