@@ -1,0 +1,184 @@
+"""The kernels' own source — the CUDA translation unit the expression compiler emits for a skill plus
+csrc/clik_pinv.cuh / clik_qp.cuh / clik_math.cuh — compiled for the HOST with g++ and a page of shims
+(one "thread", grid-stride loop over all instances) and run on the reference-generated fixture
+tests/golden/controller_vectors.json.  Like test_qp_core_host.py this is a harness for the device code's
+logic in a container without a GPU, not a product path (the product has no CPU fallback); the GPU tests
+run the same source as sm_100a code against the same fixture (test_gpu_golden.py)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import casclik_b200 as cc
+from oracle_bridge import close, orc
+from test_golden_controllers import PINV, QP, VECTORS, load_case, golden_velocities, golden_qp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = r'''
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#define __device__
+#define __host__
+#define __global__
+#define __constant__ static const
+#define __forceinline__ inline
+#define __noinline__
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(n)
+#define __shared__ static
+struct D1 { unsigned x = 1, y = 1, z = 1; };
+struct D0 { unsigned x = 0, y = 0, z = 0; };
+static D1 gridDim, blockDim;
+static D0 blockIdx, threadIdx;
+template <class T> static inline T __ldcs(const T* p) { return *p; }
+template <class T> static inline void __stcs(T* p, T v) { *p = v; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
+static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline int __double2int_rn(double x) { return (int)std::nearbyint(x); }
+static inline unsigned __activemask() { return 1u; }
+static inline int __any_sync(unsigned, int p) { return p; }
+static inline void __syncthreads() {}
+static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+using std::fma; using std::fmax; using std::fmin; using std::fabs; using std::sqrt;
+#define __CUDACC__ 1   // (after the standard headers) enables the shared-memory tail pass of clik_qp.cuh
+'''
+
+
+def _host_library(ctrl, tmp_path):
+    ctrl.setup_problem_functions(load=False)
+    cu = ctrl.cubin_path[:-len(".cubin")] + ".cu"
+    text = open(cu).read().replace("__device__ const unsigned short", "static const unsigned short")
+    src = tmp_path / "skill.cpp"
+    src.write_text(SHIM + text)
+    so = tmp_path / "skill.so"
+    subprocess.run(["g++", "-O0", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off",
+                    "-I", os.path.join(ROOT, "casclik_b200", "csrc"), "-o", str(so), str(src)], check=True)
+    return ctypes.CDLL(str(so))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _inputs(inp):
+    c = lambda k: np.ascontiguousarray(inp[k], dtype=np.float64) if k in inp else None  # noqa: E731
+    return c("t"), c("q"), c("x"), c("y")
+
+
+@pytest.mark.parametrize("name", PINV)
+def test_pinv_kernel_source_on_host_reproduces_the_reference_outputs(name, tmp_path):
+    spec, inp, kwargs, outputs = load_case(name)
+    ctrl = cc.PseudoInverseController(spec, **kwargs)
+    lib = _host_library(ctrl, tmp_path)
+    t, q, x, y = _inputs(inp)
+    nq, N = q.shape
+    nx = 0 if x is None else x.shape[0]
+    qdot, xdot = np.full((nq, N), np.nan), (np.full((nx, N), np.nan) if nx else None)
+    mode = np.full(N, -9, dtype=np.int32)
+    lib.clik_pinv_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), _p(qdot), _p(xdot), _p(mode))
+    got = qdot if xdot is None else np.vstack([qdot, xdot])
+    gv, gmode = golden_velocities(outputs)
+    assert np.array_equal(mode, gmode)
+    ok = close(got, gv, 1e-9, 1e-12)
+    if "kitchen_sink" in name or "conv_last" in name:        # multi-task chains, DESIGN §5
+        err = np.linalg.norm(got - gv, axis=0) / np.maximum(np.linalg.norm(gv, axis=0), 1e-300)
+        assert err.max() < 1e-9 and ok.mean() > 0.98, (err.max(), ok.mean())
+    else:
+        assert ok.all(), np.abs(got - gv).max()
+    ro = VECTORS[name].get("rollout")
+    if ro:                                                   # the closed-loop kernel, same harness
+        cfg, n = ro["config"], ro["config"]["n"]
+        qs = np.ascontiguousarray(q[:, :n])
+        xs = None if x is None else np.ascontiguousarray(x[:, :n])
+        ys = None if y is None else np.ascontiguousarray(y[:, :n])
+        ts = np.ascontiguousarray(t[:n])
+        inf = float("inf")
+        lib.clik_pinv_rollout_kernel(
+            ctypes.c_longlong(n), ctypes.c_int(cfg["steps"]), ctypes.c_double(cfg["dt"]), _p(ts), ctypes.c_int(1),
+            _p(qs), _p(xs), _p(ys), ctypes.c_double(inf if cfg["max_speed"] is None else cfg["max_speed"]),
+            ctypes.c_double(inf if cfg["max_virtual_speed"] is None else cfg["max_virtual_speed"]),
+            None, None, None, None)
+        want = np.array(ro["q_final"]).T
+        assert np.abs(qs - want).max() <= 1e-7 * (1 + np.abs(want).max())
+
+
+@pytest.mark.parametrize("name", QP)
+def test_qp_kernel_source_on_host_reproduces_the_reference_minimisers(name, tmp_path):
+    spec, inp, kwargs, outputs = load_case(name)
+    ctrl = cc.ReactiveQPController(spec, **kwargs)
+    lib = _host_library(ctrl, tmp_path)
+    t, q, x, y = _inputs(inp)
+    N = q.shape[1]
+    gx, gh, gA, glb, gub = golden_qp(outputs)
+    nqp = gx.shape[1]
+    sol = np.full((nqp, N), np.nan)
+    status = np.full(N, -9, dtype=np.int32)
+    active = np.zeros((2, N), dtype=np.uint32)
+    lib.clik_qp_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), None, None, _p(sol),
+                       _p(status), _p(active), ctypes.c_int(10 * (nqp + gA.shape[1])))
+    assert np.all(status == 0)
+    for i in range(N):
+        assert np.abs(sol[:, i] - gx[i]).max() <= 1e-7 * (1 + np.abs(gx[i]).max())
+        kk = orc.kkt_residuals(gh, gA[i], glb[i], gub[i], sol[:, i])
+        assert kk["primal"] < 1e-6 and kk["stationarity"] < 1e-6 and kk["sign"] < 1e-6
+    if ctrl.kernel_meta.get("qp_split"):                     # prediction pass + tail pass, as the ABI launches them
+        sol2, status2, active2 = np.full_like(sol, np.nan), np.full_like(status, -9), np.zeros_like(active)
+        args = (ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), None, None, _p(sol2), _p(status2),
+                _p(active2), ctypes.c_int(10 * (nqp + gA.shape[1])))
+        lib.clik_qp_fast_kernel(*args)
+        assert set(np.unique(status2)) <= {0, 3}
+        lib.clik_qp_tail_kernel(*args)
+        assert np.array_equal(sol2, sol) and np.array_equal(status2, status) and np.array_equal(active2, active)
+
+
+@pytest.mark.parametrize("name", ["ur5_track", "ur5_moe2016_pinv", "ur5_moe2016_multidim", "iiwa_multitask"])
+def test_benchmark_scenarios_kernel_source_on_host_vs_oracle(name, tmp_path):
+    """The BASELINE scenarios at a few thousand instances (all mode-selection paths: static modes, the
+    closed-form unit-set modes of the 128-mode iiwa skill, multidim sets) against the oracle."""
+    from casclik_b200 import scenarios
+    from oracle_bridge import oracle_pinv
+    sc = scenarios.get(name)
+    ctrl = sc.make_controller()
+    lib = _host_library(ctrl, tmp_path)
+    N = 3000
+    inp = {k: v for k, v in sc.sample(N, seed=17).items() if v is not None}
+    t, q, x, y = _inputs(inp)
+    nq = q.shape[0]
+    qdot, mode = np.full((nq, N), np.nan), np.full(N, -9, dtype=np.int32)
+    lib.clik_pinv_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), _p(qdot), None, _p(mode))
+    ref_v, ref_mode = oracle_pinv(sc.spec, inp, dict(sc.options) if sc.options else None)
+    assert np.array_equal(mode, ref_mode)
+    assert len(np.unique(ref_mode)) >= (1 if name == "ur5_track" else 2)
+    assert close(qdot, ref_v, 1e-9, 1e-12).all(), np.abs(qdot - ref_v).max()
+
+
+@pytest.mark.parametrize("name", ["ur5_qp", "ur5_moe2016_qp"])
+def test_benchmark_qp_scenarios_kernel_source_on_host_vs_oracle(name, tmp_path):
+    from casclik_b200 import scenarios
+    from oracle_bridge import oracle_qp_problem
+    sc = scenarios.get(name)
+    ctrl = sc.make_controller()
+    lib = _host_library(ctrl, tmp_path)
+    N = 400
+    inp = {k: v for k, v in sc.sample(N, seed=23).items() if v is not None}
+    t, q, x, y = _inputs(inp)
+    h, A, lb, ub = oracle_qp_problem(sc.spec, inp)
+    nqp, m = A.shape[2], A.shape[1]
+    sol, status = np.full((nqp, N), np.nan), np.full(N, -9, dtype=np.int32)
+    active = np.zeros((2, N), dtype=np.uint32)
+    lib.clik_qp_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), None, None, _p(sol),
+                       _p(status), _p(active), ctypes.c_int(10 * (nqp + m)))
+    assert np.all(status == 0)
+    for i in range(N):
+        xo, lamo, sto = orc.solve_qp_single(h, A[i], lb[i], ub[i])
+        assert sto == 0 and np.abs(sol[:, i] - xo).max() <= 1e-7 * (1 + np.abs(xo).max())
+        up = sum(1 << r for r in range(m) if lamo[r] > 0)
+        lo = sum(1 << r for r in range(m) if lamo[r] < 0)
+        assert (int(active[0, i]), int(active[1, i])) == (up, lo), i
