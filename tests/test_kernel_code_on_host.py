@@ -182,3 +182,63 @@ def test_benchmark_qp_scenarios_kernel_source_on_host_vs_oracle(name, tmp_path):
         up = sum(1 << r for r in range(m) if lamo[r] > 0)
         lo = sum(1 << r for r in range(m) if lamo[r] < 0)
         assert (int(active[0, i]), int(active[1, i])) == (up, lo), i
+
+
+@pytest.mark.parametrize("env", [{"CLIK_UNIT_SETS": "0"}, {"CLIK_UNIT_SETS": "0", "CLIK_NSTATIC": "1"}],
+                         ids=["29_static_then_dynamic", "all_dynamic"])
+def test_mode_search_variants_agree_with_the_oracle(env, tmp_path, monkeypatch):
+    """The mode-search implementations behind solve_instance — static register modes, the run-time search
+    over row lists in local memory (dynamic_mode), and the closed-form unit-set modes (default for this
+    skill, covered above) — on the 128-mode iiwa skill with many instances outside their limits.
+    (All 128 modes on the static path is not tried: 128 distinct template instantiations take g++ forever.)"""
+    from casclik_b200 import scenarios
+    from oracle_bridge import oracle_pinv
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    sc = scenarios.get("iiwa_multitask")
+    ctrl = sc.make_controller()
+    lib = _host_library(ctrl, tmp_path)
+    assert not ctrl.kernel_meta["pinv_unit_sets"]
+    assert ctrl.kernel_meta["pinv_static_modes"] == {"1": 1}.get(env.get("CLIK_NSTATIC"), 29)
+    N = 1500
+    inp = {k: v for k, v in sc.sample(N, seed=29).items() if v is not None}
+    # push more joints over their limits than the benchmark distribution does: deeper modes
+    rng = np.random.default_rng(5)
+    lower, upper = np.array(sc.spec.constraints[0].set_min), np.array(sc.spec.constraints[0].set_max)
+    for i in range(0, N, 3):
+        j = rng.choice(7, size=rng.integers(1, 5), replace=False)
+        inp["q"][j, i] = np.where(rng.random(len(j)) < 0.5, -3.2, 3.2)
+    t, q, x, y = _inputs(inp)
+    qdot, mode = np.full((7, N), np.nan), np.full(N, -9, dtype=np.int32)
+    lib.clik_pinv_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), _p(qdot), None, _p(mode))
+    ref_v, ref_mode = oracle_pinv(sc.spec, inp)
+    assert np.array_equal(mode, ref_mode)
+    assert len(np.unique(ref_mode)) > 40 and ref_mode.max() > 60
+    assert close(qdot, ref_v, 1e-9, 1e-12).all(), np.abs(qdot - ref_v).max()
+
+
+def test_dense_sets_take_the_dynamic_tail(tmp_path):
+    """Four SetConstraints on dense expressions (16 modes: 11 static, 5 through dynamic_mode) + two tasks."""
+    from casclik_b200 import cs
+    from oracle_bridge import oracle_pinv
+    t, q = cs.MX.sym("t"), cs.MX.sym("q", 5)
+    sets = [cc.SetConstraint("s%d" % k, e, set_min=-0.3, set_max=0.3, priority=k, gain=2.0) for k, e in enumerate(
+        [q[0] + 0.5 * q[1], cs.sin(q[1]) - q[2], q[2] * q[3], q[3] + q[4] - 0.2 * cs.cos(t)])]
+    tasks = [cc.EqualityConstraint("a", cs.vertcat(q[0] - q[4], q[1] + q[2] - 0.1), priority=8),
+             cc.VelocityEqualityConstraint("b", q[3] - q[0], target=0.1, priority=9)]
+    spec = cc.SkillSpecification("dense_sets", t, q, constraints=sets + tasks)
+    ctrl = cc.PseudoInverseController(spec)
+    lib = _host_library(ctrl, tmp_path)
+    assert ctrl.n_modes == 16 and ctrl.kernel_meta["pinv_static_modes"] == 11 and not ctrl.kernel_meta["pinv_unit_sets"]
+    N = 4000
+    rng = np.random.default_rng(8)
+    inp = {"t": rng.uniform(0, 5, N), "q": rng.uniform(-0.9, 0.9, (5, N))}
+    t_, q_, _, _ = _inputs(inp)
+    qdot, mode = np.full((5, N), np.nan), np.full(N, -9, dtype=np.int32)
+    lib.clik_pinv_kernel(ctypes.c_longlong(N), _p(t_), ctypes.c_int(1), _p(q_), None, None, _p(qdot), None, _p(mode))
+    ref_v, ref_mode = oracle_pinv(spec, inp)
+    assert np.array_equal(mode, ref_mode)
+    assert (ref_mode >= 11).sum() > 20 and (ref_mode == -1).sum() >= 0
+    ok = close(qdot, ref_v, 1e-9, 1e-12)
+    err = np.linalg.norm(qdot - ref_v, axis=0) / np.maximum(np.linalg.norm(ref_v, axis=0), 1e-300)
+    assert ok.mean() > 0.995 and err[np.isfinite(err)].max() < 1e-8, (ok.mean(), err.max())
