@@ -1,0 +1,62 @@
+"""Random skills for differential testing of the whole stack (expression layer -> lowering -> emitted
+CUDA -> kernel headers) against the oracle: random smooth expressions of q / t / virtual / input
+variables in 1-4 constraints of every class, random priorities, gains and options."""
+import numpy as np
+
+import casclik_b200 as cc
+from casclik_b200 import cs
+
+
+def rand_expr(rng, syms, depth=0):
+    """random smooth scalar expression of the given symbols"""
+    pick = rng.integers(0, 6)
+    a = syms[rng.integers(len(syms))]
+    b = syms[rng.integers(len(syms))]
+    c = float(rng.uniform(-1, 1))
+    if pick == 0: return a + c * b
+    if pick == 1: return cs.sin(a) + c * b
+    if pick == 2: return a * b + c
+    if pick == 3: return cs.cos(a + b) * c + a
+    if pick == 4: return a - c * cs.sin(b) * a
+    return c * a + 0.5 * b * b
+
+def make_skill(seed):
+    rng = np.random.default_rng(seed)
+    nq = int(rng.integers(2, 6))
+    t, q = cs.MX.sym("t"), cs.MX.sym("q", nq)
+    has_x, has_y = rng.random() < 0.35, rng.random() < 0.4
+    x = cs.MX.sym("x") if has_x else None
+    y = cs.MX.sym("y", 2) if has_y else None
+    syms = [q[i] for i in range(nq)] + ([x] if has_x else []) + ([y[0], y[1]] if has_y else [])
+    syms_t = syms + [t]
+    cons = []
+    n_cons = int(rng.integers(1, 5))
+    n_sets = 0
+    for k in range(n_cons):
+        kind = rng.choice(["eq", "eq", "set", "set", "veleq"])
+        prio = int(rng.integers(0, 6))
+        if kind == "eq":
+            rows = int(rng.integers(1, 4))
+            e = cs.vertcat(*[rand_expr(rng, syms_t) for _ in range(rows)])
+            gain = float(rng.uniform(0.5, 3.0)) if rng.random() < 0.7 else np.diag(rng.uniform(0.5, 2.0, rows))
+            cons.append(cc.EqualityConstraint("eq%d" % k, e, gain=gain, priority=prio))
+        elif kind == "set" and n_sets < 4:
+            n_sets += 1
+            e = syms[rng.integers(nq)] if rng.random() < 0.5 else rand_expr(rng, syms_t)
+            lo = float(rng.uniform(-0.6, 0.0)); hi = lo + float(rng.uniform(0.2, 0.8))
+            cons.append(cc.SetConstraint("set%d" % k, e, set_min=lo, set_max=hi, gain=float(rng.uniform(0.5, 3)), priority=prio))
+        else:
+            e = rand_expr(rng, syms)
+            cons.append(cc.VelocityEqualityConstraint("vel%d" % k, e, target=float(rng.uniform(-0.3, 0.3)), priority=prio))
+    if not any(isinstance(c, (cc.EqualityConstraint, cc.VelocityEqualityConstraint)) for c in cons):
+        cons.append(cc.EqualityConstraint("eq_last", rand_expr(rng, syms_t), priority=9))
+    kw = dict(virtual_var=x, input_var=y)
+    spec = cc.SkillSpecification("fuzz%d" % seed, t, q, constraints=cons, **{k: v for k, v in kw.items() if v is not None})
+    opts = {}
+    if rng.random() < 0.5: opts["damping_factor"] = 1e-4
+    if rng.random() < 0.3: opts["feedforward"] = False
+    N = 400
+    inp = {"t": rng.uniform(0, 3, N), "q": rng.uniform(-0.9, 0.9, (nq, N))}
+    if has_x: inp["x"] = rng.uniform(-0.9, 0.9, (1, N))
+    if has_y: inp["y"] = rng.uniform(-0.9, 0.9, (2, N))
+    return spec, opts, inp
