@@ -60,3 +60,55 @@ def make_skill(seed):
     if has_x: inp["x"] = rng.uniform(-0.9, 0.9, (1, N))
     if has_y: inp["y"] = rng.uniform(-0.9, 0.9, (2, N))
     return spec, opts, inp
+
+
+def make_qp_skill(seed):
+    """Random skill for the QP controller: every constraint class, hard and soft, random weights."""
+    rng = np.random.default_rng(10_000 + seed)
+    nq = int(rng.integers(2, 6))
+    t, q, dq = cs.MX.sym("t"), cs.MX.sym("q", nq), cs.MX.sym("dq", nq)
+    has_x, has_y = rng.random() < 0.35, rng.random() < 0.4
+    x, dx = (cs.MX.sym("x"), cs.MX.sym("dx")) if has_x else (None, None)
+    y = cs.MX.sym("y", 2) if has_y else None
+    syms = [q[i] for i in range(nq)] + ([x] if has_x else []) + ([y[0], y[1]] if has_y else [])
+    syms_t = syms + [t]
+    cons = []
+    for k in range(int(rng.integers(1, 5))):
+        kind = rng.choice(["eq", "set", "veleq", "velset", "limits"])
+        soft = "soft" if rng.random() < 0.6 else "hard"
+        sw = float(rng.uniform(0.5, 3.0))
+        if kind == "eq":
+            rows = int(rng.integers(1, 3))
+            e = cs.vertcat(*[rand_expr(rng, syms_t) for _ in range(rows)])
+            cons.append(cc.EqualityConstraint("eq%d" % k, e, gain=float(rng.uniform(0.5, 3.0)), constraint_type="soft",
+                                              slack_weight=sw))
+        elif kind == "set":
+            e = rand_expr(rng, syms_t)
+            lo = float(rng.uniform(-0.6, 0.0))
+            cons.append(cc.SetConstraint("set%d" % k, e, set_min=lo, set_max=lo + float(rng.uniform(0.3, 0.9)),
+                                         gain=float(rng.uniform(0.5, 2.0)), constraint_type=soft, slack_weight=sw))
+        elif kind == "veleq":
+            cons.append(cc.VelocityEqualityConstraint("vel%d" % k, rand_expr(rng, syms), target=float(rng.uniform(-0.3, 0.3)),
+                                                      constraint_type="soft", slack_weight=sw))
+        elif kind == "velset":
+            cons.append(cc.VelocitySetConstraint("spd%d" % k, q, set_min=-float(rng.uniform(0.3, 1.0)) * np.ones(nq),
+                                                 set_max=float(rng.uniform(0.3, 1.0)) * np.ones(nq)))
+        else:
+            cons.append(cc.SetConstraint("lim%d" % k, q, set_min=-np.ones(nq), set_max=np.ones(nq),
+                                         gain=float(rng.uniform(0.5, 2.0))))
+    kw = {"robot_vel_var": dq}
+    if has_x:
+        kw.update(virtual_var=x, virtual_vel_var=dx)
+    if has_y:
+        kw["input_var"] = y
+    spec = cc.SkillSpecification("qpfuzz%d" % seed, t, q, constraints=cons, **kw)
+    weights = {}
+    if rng.random() < 0.5:
+        weights["robot_var_weights"] = [float(v) for v in rng.uniform(0.5, 2.0, nq)]
+    N = 200
+    inp = {"t": rng.uniform(0, 3, N), "q": rng.uniform(-0.9, 0.9, (nq, N))}
+    if has_x:
+        inp["x"] = rng.uniform(-0.9, 0.9, (1, N))
+    if has_y:
+        inp["y"] = rng.uniform(-0.9, 0.9, (2, N))
+    return spec, weights, inp

@@ -269,3 +269,34 @@ def test_fuzzed_skills_kernel_source_on_host_vs_oracle(seed, tmp_path):
     assert np.array_equal(mode, ref_mode)
     err = np.linalg.norm(got - ref_v, axis=0) / np.maximum(np.linalg.norm(ref_v, axis=0), 1e-12)
     assert err.max() < 1e-7, err.max()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzzed_qp_skills_kernel_source_on_host_vs_oracle(seed, tmp_path):
+    """Random QP skills (hard / soft rows of every constraint class, random weights; some are infeasible for
+    part of the batch): status, minimiser and working-set masks against the oracle's solve of the same problem."""
+    from fuzz_skills import make_qp_skill
+    from oracle_bridge import oracle_qp_problem
+    spec, weights, inp = make_qp_skill(seed)
+    ctrl = cc.ReactiveQPController(spec, **weights)
+    lib = _host_library(ctrl, tmp_path)
+    t, q, x, y = _inputs(inp)
+    N = q.shape[1]
+    if ctrl._nxv and x is None:
+        x = np.zeros((ctrl._nxv, N))
+        inp = dict(inp, x=x)
+    w = {"w_rob": weights["robot_var_weights"]} if "robot_var_weights" in weights else {}
+    h, A, lb, ub = oracle_qp_problem(spec, inp, **w)
+    m, nqp = A.shape[1], A.shape[2]
+    sol, status = np.full((nqp, N), np.nan), np.full(N, -9, dtype=np.int32)
+    active = np.zeros((2, N), dtype=np.uint32)
+    lib.clik_qp_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y if ctrl._ny else None), None, None,
+                       _p(sol), _p(status), _p(active), ctypes.c_int(10 * (nqp + m)))
+    for i in range(N):
+        xo, lamo, sto = orc.solve_qp_single(h, A[i], lb[i], ub[i])
+        assert sto == int(status[i]), i
+        if sto == 0:
+            assert np.abs(sol[:, i] - xo).max() <= 1e-7 * (1 + np.abs(xo).max()), i
+            up = sum(1 << r for r in range(m) if lamo[r] > 0)
+            lo = sum(1 << r for r in range(m) if lamo[r] < 0)
+            assert (int(active[0, i]), int(active[1, i])) == (up, lo), i
