@@ -52,9 +52,16 @@ using std::fma; using std::fmax; using std::fmin; using std::fabs; using std::sq
 
 
 def _host_library(ctrl, tmp_path):
-    ctrl.setup_problem_functions(load=False)
-    cu = ctrl.cubin_path[:-len(".cubin")] + ".cu"
-    text = open(cu).read().replace("__device__ const unsigned short", "static const unsigned short")
+    """Lower + emit the skill (no nvcc: the host only needs the generated source), build it with g++."""
+    from casclik_b200 import build
+    saved = (build.compile_cubin, build.kernel_registers)
+    build.compile_cubin = lambda source, tag="skill", **kw: (b"", os.path.join(str(tmp_path), "skill.cubin"))
+    build.kernel_registers = lambda *a, **kw: None
+    try:
+        ctrl.setup_problem_functions(load=False)
+    finally:
+        build.compile_cubin, build.kernel_registers = saved
+    text = ctrl.kernel_source.replace("__device__ const unsigned short", "static const unsigned short")
     src = tmp_path / "skill.cpp"
     src.write_text(SHIM + text)
     so = tmp_path / "skill.so"
