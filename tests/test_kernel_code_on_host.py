@@ -135,6 +135,22 @@ def test_qp_kernel_source_on_host_reproduces_the_reference_minimisers(name, tmp_
         assert np.abs(sol[:, i] - gx[i]).max() <= 1e-7 * (1 + np.abs(gx[i]).max())
         kk = orc.kkt_residuals(gh, gA[i], glb[i], gub[i], sol[:, i])
         assert kk["primal"] < 1e-6 and kk["stationarity"] < 1e-6 and kk["sign"] < 1e-6
+    ro = VECTORS[name].get("rollout")
+    if ro:                                                   # closed loop, warm-started from step to step
+        cfg, n = ro["config"], ro["config"]["n"]
+        qs = np.ascontiguousarray(q[:, :n])
+        xs = None if x is None else np.ascontiguousarray(x[:, :n])
+        ys = None if y is None else np.ascontiguousarray(y[:, :n])
+        ts = np.ascontiguousarray(t[:n])
+        failed = np.full(n, -9, dtype=np.int32)
+        inf = float("inf")
+        lib.clik_qp_rollout_kernel(
+            ctypes.c_longlong(n), ctypes.c_int(cfg["steps"]), ctypes.c_double(cfg["dt"]), _p(ts), ctypes.c_int(1),
+            _p(qs), _p(xs), _p(ys), ctypes.c_double(inf if cfg["max_speed"] is None else cfg["max_speed"]),
+            ctypes.c_double(inf if cfg["max_virtual_speed"] is None else cfg["max_virtual_speed"]),
+            None, _p(failed), ctypes.c_int(10 * (nqp + gA.shape[1])))
+        want = np.array(ro["q_final"]).T
+        assert np.all(failed == 0) and np.abs(qs - want).max() <= 1e-7 * (1 + np.abs(want).max())
     if ctrl.kernel_meta.get("qp_split"):                     # prediction pass + tail pass, as the ABI launches them
         sol2, status2, active2 = np.full_like(sol, np.nan), np.full_like(status, -9), np.zeros_like(active)
         args = (ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), None, None, _p(sol2), _p(status2),
