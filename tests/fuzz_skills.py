@@ -112,3 +112,26 @@ def make_qp_skill(seed):
     if has_y:
         inp["y"] = rng.uniform(-0.9, 0.9, (2, N))
     return spec, weights, inp
+
+
+def make_dense_qp_skill(seed):
+    """More than 6 dense rows (or more than 12 variables): the generic in-kernel QP solver."""
+    rng = np.random.default_rng(20_000 + seed)
+    nq = int(rng.integers(3, 6))
+    t, q, dq = cs.MX.sym("t"), cs.MX.sym("q", nq), cs.MX.sym("dq", nq)
+    syms_t = [q[i] for i in range(nq)] + [t]
+    cons = []
+    for k in range(4):
+        rows = int(rng.integers(2, 4))
+        e = cs.vertcat(*[rand_expr(rng, syms_t) for _ in range(rows)])
+        if k < 2:
+            cons.append(cc.EqualityConstraint("eq%d" % k, e, gain=float(rng.uniform(0.5, 3.0)), constraint_type="soft",
+                                              slack_weight=float(rng.uniform(0.5, 3.0))))
+        else:
+            lo = rng.uniform(-0.6, 0.0, rows)
+            cons.append(cc.SetConstraint("set%d" % k, e, set_min=lo, set_max=lo + rng.uniform(0.3, 0.9, rows),
+                                         gain=float(rng.uniform(0.5, 2.0)), constraint_type="soft"))
+    cons.append(cc.VelocitySetConstraint("spd", q, set_min=-np.ones(nq), set_max=np.ones(nq)))
+    spec = cc.SkillSpecification("qpdense%d" % seed, t, q, robot_vel_var=dq, constraints=cons)
+    N = 120
+    return spec, {}, {"t": rng.uniform(0, 3, N), "q": rng.uniform(-0.9, 0.9, (nq, N))}

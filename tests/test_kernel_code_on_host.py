@@ -294,15 +294,18 @@ def test_fuzzed_skills_kernel_source_on_host_vs_oracle(seed, tmp_path):
     assert err.max() < 1e-7, err.max()
 
 
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", list(range(8)) + ["dense0", "dense1", "dense2"])
 def test_fuzzed_qp_skills_kernel_source_on_host_vs_oracle(seed, tmp_path):
     """Random QP skills (hard / soft rows of every constraint class, random weights; some are infeasible for
-    part of the batch): status, minimiser and working-set masks against the oracle's solve of the same problem."""
-    from fuzz_skills import make_qp_skill
+    part of the batch): status, minimiser and working-set masks against the oracle's solve of the same problem.
+    The "dense" seeds have 8-10 dense rows and 12-15 variables: the generic in-kernel solver."""
+    from fuzz_skills import make_qp_skill, make_dense_qp_skill
     from oracle_bridge import oracle_qp_problem
-    spec, weights, inp = make_qp_skill(seed)
+    dense = isinstance(seed, str)
+    spec, weights, inp = make_dense_qp_skill(int(seed[5:])) if dense else make_qp_skill(seed)
     ctrl = cc.ReactiveQPController(spec, **weights)
     lib = _host_library(ctrl, tmp_path)
+    assert bool(ctrl.kernel_meta["qp_structured"]) != dense
     t, q, x, y = _inputs(inp)
     N = q.shape[1]
     if ctrl._nxv and x is None:
