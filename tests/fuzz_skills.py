@@ -135,3 +135,34 @@ def make_dense_qp_skill(seed):
     spec = cc.SkillSpecification("qpdense%d" % seed, t, q, robot_vel_var=dq, constraints=cons)
     N = 120
     return spec, {}, {"t": rng.uniform(0, 3, N), "q": rng.uniform(-0.9, 0.9, (nq, N))}
+
+
+def make_option_skill(seed):
+    """Skills for the two experimental pinv options: vector-valued sets with multidim_sets, or a final
+    SetConstraint with converge_final_set_to_max."""
+    rng = np.random.default_rng(30_000 + seed)
+    nq = int(rng.integers(3, 6))
+    t, q = cs.MX.sym("t"), cs.MX.sym("q", nq)
+    syms_t = [q[i] for i in range(nq)] + [t]
+    multidim = seed % 2 == 0
+    cons = [cc.EqualityConstraint("task", cs.vertcat(*[rand_expr(rng, syms_t) for _ in range(int(rng.integers(1, 3)))]),
+                                  gain=float(rng.uniform(0.5, 2.0)), priority=5)]
+    if multidim:
+        for k in range(int(rng.integers(1, 3))):
+            rows = int(rng.integers(2, 4))
+            e = cs.vertcat(*[rand_expr(rng, syms_t) for _ in range(rows)])
+            lo = rng.uniform(-0.6, 0.0, rows)
+            cons.append(cc.SetConstraint("box%d" % k, e, set_min=lo, set_max=lo + rng.uniform(0.3, 0.9, rows),
+                                         gain=float(rng.uniform(0.5, 3.0)), priority=int(rng.integers(0, 5))))
+        opts = {"multidim_sets": True}
+    else:
+        cons.append(cc.SetConstraint("mid", rand_expr(rng, syms_t), set_min=-0.4, set_max=0.3, priority=2))
+        lo = float(rng.uniform(-0.6, 0.0))
+        cons.append(cc.SetConstraint("final", rand_expr(rng, syms_t), set_min=lo, set_max=lo + float(rng.uniform(0.3, 0.9)),
+                                     gain=float(rng.uniform(0.5, 3.0)), priority=9))
+        opts = {"converge_final_set_to_max": True}
+    if rng.random() < 0.5:
+        opts["damping_factor"] = 1e-4
+    spec = cc.SkillSpecification("optfuzz%d" % seed, t, q, constraints=cons)
+    N = 400
+    return spec, opts, {"t": rng.uniform(0, 3, N), "q": rng.uniform(-0.9, 0.9, (nq, N))}

@@ -326,3 +326,23 @@ def test_fuzzed_qp_skills_kernel_source_on_host_vs_oracle(seed, tmp_path):
             up = sum(1 << r for r in range(m) if lamo[r] > 0)
             lo = sum(1 << r for r in range(m) if lamo[r] < 0)
             assert (int(active[0, i]), int(active[1, i])) == (up, lo), i
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzzed_option_skills_kernel_source_on_host_vs_oracle(seed, tmp_path):
+    """Random skills for the experimental options: vector-valued sets with multidim_sets (even seeds),
+    a final SetConstraint with converge_final_set_to_max (odd seeds).  Modes bit-exact; 1e-6 on the
+    velocities because random 3-row boxes on 3 joints are over-determined (24 seeds: worst 2e-7)."""
+    from fuzz_skills import make_option_skill
+    from oracle_bridge import oracle_pinv
+    spec, opts, inp = make_option_skill(seed)
+    ctrl = cc.PseudoInverseController(spec, options=dict(opts))
+    lib = _host_library(ctrl, tmp_path)
+    t, q, x, y = _inputs(inp)
+    nq, N = q.shape
+    qdot, mode = np.full((nq, N), np.nan), np.full(N, -9, dtype=np.int32)
+    lib.clik_pinv_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), None, None, _p(qdot), None, _p(mode))
+    ref_v, ref_mode = oracle_pinv(spec, inp, dict(opts))
+    assert np.array_equal(mode, ref_mode) and len(np.unique(ref_mode)) >= 2
+    err = np.linalg.norm(qdot - ref_v, axis=0) / np.maximum(np.linalg.norm(ref_v, axis=0), 1e-12)
+    assert err.max() < 1e-6, err.max()
