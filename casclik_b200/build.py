@@ -5,6 +5,8 @@ package directory (`csrc/libclik_b200.so`, `_cache/<hash>.cubin`) so they travel
 tree.  This replaces the reference's per-function shell JIT (`jit: True`, `-O2`; reference
 casclik/controllers/pseudo_inverse.py:59-65) with one cached compile per skill.
 """
+import contextlib
+import fcntl
 import hashlib
 import os
 import shutil
@@ -44,6 +46,24 @@ def _newer(target, sources):
     return all(os.path.getmtime(s) <= t for s in sources)
 
 
+@contextlib.contextmanager
+def _build_lock(directory):
+    """Serialises builds between processes (torchrun ranks all reach setup at the same moment):
+    an exclusive fcntl lock on a file in the artefact directory.  Everything a build writes goes
+    to a pid-suffixed temporary first and is renamed into place, so a reader outside the lock
+    (another rank's dlopen, a cached-cubin read) never sees a half-written file."""
+    os.makedirs(directory, exist_ok=True)
+    fd = os.open(os.path.join(directory, ".build.lock"), os.O_CREAT | os.O_RDWR, 0o644)
+    try:
+        fcntl.flock(fd, fcntl.LOCK_EX)
+        yield
+    finally:
+        try:
+            fcntl.flock(fd, fcntl.LOCK_UN)
+        finally:
+            os.close(fd)
+
+
 def library_sources():
     return [os.path.join(CSRC_DIR, f) for f in ("clik_abi.cu", "clik_qp.cuh")] + \
            [os.path.join(os.path.dirname(PKG_DIR), "include", "clik.h")]
@@ -54,14 +74,23 @@ def build_library(force=False, verbose=False):
     srcs = library_sources()
     if not force and _newer(LIB_PATH, srcs):
         return LIB_PATH
-    cmd = [nvcc_path()] + ARCH_FLAGS + COMMON_FLAGS + [
-        "-shared", "-Xcompiler", "-fPIC", "-cudart", "static",
-        "-o", LIB_PATH, os.path.join(CSRC_DIR, "clik_abi.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    out = _run(cmd, "building libclik_b200.so")
-    if verbose:
-        print(out)
+    with _build_lock(CSRC_DIR):
+        if not force and _newer(LIB_PATH, srcs):      # another process built it while we waited
+            return LIB_PATH
+        tmp = LIB_PATH + ".tmp%d" % os.getpid()
+        cmd = [nvcc_path()] + ARCH_FLAGS + COMMON_FLAGS + [
+            "-shared", "-Xcompiler", "-fPIC", "-cudart", "static",
+            "-o", tmp, os.path.join(CSRC_DIR, "clik_abi.cu")]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        try:
+            out = _run(cmd, "building libclik_b200.so")
+            os.replace(tmp, LIB_PATH)
+        finally:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+        if verbose:
+            print(out)
     return LIB_PATH
 
 
@@ -87,18 +116,30 @@ def compile_cubin(source: str, tag: str = "skill", keep_source=True, extra_flags
     base = os.path.join(CACHE_DIR, "%s_%s" % (safe, key))
     cubin = base + ".cubin"
     if not os.path.exists(cubin):
-        cu = base + ".cu"
-        with open(cu, "w") as f:
-            f.write(source)
-        tmp = cubin + ".tmp%d" % os.getpid()
-        cmd = [nvcc_path()] + ARCH_FLAGS + COMMON_FLAGS + list(extra_flags) + [
-            "-cubin", "-I", CSRC_DIR, "-Xptxas=-v", "-o", tmp, cu]
-        log = _run(cmd, "compiling skill %s" % tag)
-        with open(base + ".log", "w") as f:
-            f.write(log)
-        os.replace(tmp, cubin)
-        if not keep_source:
-            os.remove(cu)
+        with _build_lock(CACHE_DIR):
+            if not os.path.exists(cubin):             # not built by another process meanwhile
+                pid = os.getpid()
+                cu, cu_tmp = base + ".cu", base + ".tmp%d.cu" % pid
+                tmp, log_tmp = cubin + ".tmp%d" % pid, base + ".log.tmp%d" % pid
+                try:
+                    # the source is renamed into place BEFORE nvcc runs so that -lineinfo records
+                    # the path that stays on disk (ncu's source page); only the lock holder writes it
+                    with open(cu_tmp, "w") as f:
+                        f.write(source)
+                    os.replace(cu_tmp, cu)
+                    cmd = [nvcc_path()] + ARCH_FLAGS + COMMON_FLAGS + list(extra_flags) + [
+                        "-cubin", "-I", CSRC_DIR, "-Xptxas=-v", "-o", tmp, cu]
+                    log = _run(cmd, "compiling skill %s" % tag)
+                    with open(log_tmp, "w") as f:
+                        f.write(log)
+                    os.replace(log_tmp, base + ".log")
+                    os.replace(tmp, cubin)            # last: its existence marks the entry complete
+                    if not keep_source:
+                        os.remove(cu)
+                finally:
+                    for leftover in (cu_tmp, tmp, log_tmp):
+                        if os.path.exists(leftover):
+                            os.remove(leftover)
     with open(cubin, "rb") as f:
         return f.read(), cubin
 

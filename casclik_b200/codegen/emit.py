@@ -179,7 +179,8 @@ class Emitter(object):
             test = " && ".join("clik::sincos_in_range(%s)" % arg for _, arg, _, _ in g)
             fix = ["if (!(%s)) {" % test]
             for _, arg, sv, cv in g:
-                fix.append("  if (!clik::sincos_in_range(%s)) clik::sincos_slow(%s, &%s, &%s);" % (arg, arg, sv, cv))
+                fix.append("  if (!clik::sincos_in_range(%s)) { const clik::SinCos sc_ = clik::sincos_slow(%s); %s = sc_.s; %s = sc_.c; }"
+                           % (arg, arg, sv, cv))
             fix.append("}")
             out[first:last + 1] = moved + fix + rest
         return out
@@ -548,57 +549,57 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
     bounds = "__launch_bounds__(%d%s)" % (block_threads, (", %d" % min_blocks) if min_blocks else "")
     if pinv is not None:
         out.append('extern "C" __global__ void %s clik_pinv_kernel(' % bounds)
-        out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
+        out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
         out.append("    const double* y, double* qdot, double* xdot, int* mode) {")
         unroll = int(os.environ.get("CLIK_UNROLL", "1"))
         meta["pinv_unroll"] = unroll
         pf = int(os.environ.get("CLIK_PREFETCH_CTAS", "0"))
         meta["pinv_prefetch_ctas"] = pf
-        out.append("  clik::pinv_step<Skill, %d, %d>(N, t, t_stride, q, x, y, qdot, xdot, mode);" % (unroll, pf))
+        out.append("  clik::pinv_step<Skill, %d, %d>(N, ld, t, t_stride, q, x, y, qdot, xdot, mode);" % (unroll, pf))
         out.append("}")
         out.append('extern "C" __global__ void %s clik_pinv_rollout_kernel(' % bounds)
-        out.append("    long long N, int steps, double dt, const double* t0, int t_stride, double* q, double* x,")
+        out.append("    long long N, long long ld, int steps, double dt, const double* t0, int t_stride, double* q, double* x,")
         out.append("    const double* y, double vmax_q, double vmax_x, double* qdot_last, double* xdot_last,")
         out.append("    int* mode_last, int* n_failed) {")
-        out.append("  clik::pinv_rollout<Skill>(N, steps, dt, t0, t_stride, q, x, y, vmax_q, vmax_x, qdot_last,")
+        out.append("  clik::pinv_rollout<Skill>(N, ld, steps, dt, t0, t_stride, q, x, y, vmax_q, vmax_x, qdot_last,")
         out.append("                            xdot_last, mode_last, n_failed);")
         out.append("}")
         if os.environ.get("CLIK_TMA", "0") == "1":
             # opt-in TMA-staged persistent variant (measured slower than the plain kernel)
             out.append('extern "C" __global__ void %s clik_pinv_tma_kernel(' % bounds)
-            out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
+            out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
             out.append("    const double* y, double* qdot, double* xdot, int* mode) {")
-            out.append("  clik::pinv_step_tma<Skill, %d, %d>(N, t, t_stride, q, x, y, qdot, xdot, mode);"
+            out.append("  clik::pinv_step_tma<Skill, %d, %d>(N, ld, t, t_stride, q, x, y, qdot, xdot, mode);"
                        % (block_threads, int(os.environ.get("CLIK_STAGES", "2"))))
             out.append("}")
     if qp is not None:
         qmin = int(os.environ.get("CLIK_QP_MINBLOCKS", "0"))
         qbounds = "__launch_bounds__(%d%s)" % (block_threads, (", %d" % qmin) if qmin else "")
         out.append('extern "C" __global__ void %s clik_qp_kernel(' % qbounds)
-        out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
+        out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
         out.append("    const double* y, const double* x0, const unsigned* active0, double* sol, int* status,")
         out.append("    unsigned* active, int max_iter) {")
-        out.append("  clik::qp_step<Skill, clik::QP_FULL>(N, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
+        out.append("  clik::qp_step<Skill, clik::QP_FULL>(N, ld, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
         out.append("}")
         if meta.get("qp_split"):
             # fast pass (working-set prediction only) + tail pass (full solver on what it left pending)
             out.append('extern "C" __global__ void __launch_bounds__(%d) clik_qp_fast_kernel(' % block_threads)
-            out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
+            out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
             out.append("    const double* y, const double* x0, const unsigned* active0, double* sol, int* status,")
             out.append("    unsigned* active, int max_iter) {")
-            out.append("  clik::qp_step<Skill, clik::QP_FAST>(N, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
+            out.append("  clik::qp_step<Skill, clik::QP_FAST>(N, ld, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
             out.append("}")
             out.append('extern "C" __global__ void %s clik_qp_tail_kernel(' % qbounds)
-            out.append("    long long N, const double* t, int t_stride, const double* q, const double* x,")
+            out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
             out.append("    const double* y, const double* x0, const unsigned* active0, double* sol, int* status,")
             out.append("    unsigned* active, int max_iter) {")
-            out.append("  clik::qp_step_tail<Skill>(N, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
+            out.append("  clik::qp_step_tail<Skill>(N, ld, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
             out.append("}")
     if qp is not None:
         out.append('extern "C" __global__ void __launch_bounds__(%d) clik_qp_rollout_kernel(' % block_threads)
-        out.append("    long long N, int steps, double dt, const double* t0, int t_stride, double* q, double* x,")
+        out.append("    long long N, long long ld, int steps, double dt, const double* t0, int t_stride, double* q, double* x,")
         out.append("    const double* y, double vmax_q, double vmax_x, double* sol_last, int* n_failed, int max_iter) {")
-        out.append("  clik::qp_rollout<Skill>(N, steps, dt, t0, t_stride, q, x, y, vmax_q, vmax_x, sol_last, n_failed,")
+        out.append("  clik::qp_rollout<Skill>(N, ld, steps, dt, t0, t_stride, q, x, y, vmax_q, vmax_x, sol_last, n_failed,")
         out.append("                          max_iter);")
         out.append("}")
     out.append('extern "C" __global__ void clik_sizes_kernel(int* o) {')

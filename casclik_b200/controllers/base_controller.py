@@ -15,6 +15,33 @@ class BaseController(object):
         return "%s<%s>" % (self.controller_type, self.skill_spec.label)
 
 
+def resolve_devices(devices):
+    """`devices` argument of solve_batch -> list of CUDA ordinals, or None for "the default device".
+    "all": every visible GPU; an int n: devices 0..n-1; a sequence: those ordinals."""
+    if devices is None:
+        return None
+    if isinstance(devices, str):
+        if devices != "all":
+            raise ValueError('devices must be None, "all", a count or a list of CUDA ordinals')
+        n = runtime.device_count()
+        if n < 1:
+            runtime.require_device()
+        return list(range(n))
+    if isinstance(devices, int):
+        if devices < 1 or devices > runtime.device_count():
+            raise ValueError("devices=%d but %d CUDA devices are visible" % (devices, runtime.device_count()))
+        return list(range(devices))
+    devs = [int(d) for d in devices]
+    if not devs or len(set(devs)) != len(devs):
+        raise ValueError("devices must be a non-empty list of distinct CUDA ordinals")
+    return devs
+
+
+def skill_handle_array(skills):
+    arr = (ctypes.c_void_p * len(skills))(*[s.handle for s in skills])
+    return arr
+
+
 def as_vector(value, n, what):
     """float / list / ndarray / DM -> float64 array of length n."""
     if isinstance(value, cs.GenericMatrixCommon):
@@ -51,6 +78,8 @@ class Batch(object):
             self.t_stride = 0 if t.numel() == 1 else 1
             if self.t_stride and t.numel() != self.N:
                 raise ValueError("time_var batch must have N entries")
+            if t.device != q.device:
+                raise ValueError("time_var lives on %s, robot_var on %s" % (t.device, q.device))
             self.t = t
             self.tp = runtime.dev_ptr(t, "f64", t.numel(), "time_var")
             self.qp = runtime.dev_ptr(q, "f64", n_rob * self.N, "robot_var")
@@ -75,6 +104,8 @@ class Batch(object):
     def _dev(self, a, rows, what):
         if rows == 0:
             return None
+        if a is not None and (not runtime._is_torch(a) or a.device != self.device):
+            raise ValueError("%s must be a CUDA tensor on %s like robot_var" % (what, self.device))
         if a is None:
             a = self.torch.zeros((rows, self.N), dtype=self.torch.float64, device=self.device)
             self._zeros = getattr(self, "_zeros", []) + [a]
@@ -107,6 +138,28 @@ class Batch(object):
         if self.on_device:
             return ctypes.c_void_p(arr.data_ptr())
         return ctypes.c_void_p(arr.ctypes.data)
+
+    def out_ptr(self, arr, rows, dtype, what):
+        """Validated pointer of an output buffer (rows, N) — (N,) when rows == 0 — that the kernel
+        writes in place: dtype, element count, contiguity and (device path) the device must match,
+        because a wrong buffer would be an out-of-bounds write, not an exception."""
+        if arr is None:
+            return None
+        numel = (rows if rows > 0 else 1) * self.N
+        if self.on_device:
+            if not runtime._is_torch(arr):
+                raise runtime.ClikError("%s must be a CUDA tensor when the inputs are CUDA tensors" % what)
+            if arr.device != self.device:
+                raise runtime.ClikError("%s lives on %s, the inputs on %s" % (what, arr.device, self.device))
+            return runtime.dev_ptr(arr, {"f64": "f64", "i32": "i32"}[dtype], numel, what)
+        return runtime.host_out_ptr(arr, {"f64": np.float64, "i32": np.int32}[dtype], numel, what)
+
+    @property
+    def device_index(self):
+        """CUDA ordinal the batch runs on: the tensors' device, or the default for host arrays."""
+        if self.on_device:
+            return self.device.index if self.device.index is not None else self.torch.cuda.current_device()
+        return runtime.current_device()
 
     def stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)

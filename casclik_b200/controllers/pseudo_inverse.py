@@ -21,7 +21,8 @@ from .. import sym as cs
 from ..codegen import PinvProgram, emit_skill
 from ..constraints import SetConstraint
 from ._modes import activation_map
-from .base_controller import BaseController, Batch, as_vector, dm_column
+from .base_controller import (BaseController, Batch, as_vector, dm_column, resolve_devices,
+                              skill_handle_array)
 
 
 class PseudoInverseController(BaseController):
@@ -121,7 +122,7 @@ class PseudoInverseController(BaseController):
         self._cubin = cubin
         self._compiled = None
         if load:
-            self._compiled = runtime.CompiledSkill(cubin, meta, n_slack=self.skill_spec.n_slack_var)
+            self._skill()
 
     def setup_initial_problem_solver(self):
         """Nothing to set up (same as the reference, pseudo_inverse.py:485-488)."""
@@ -138,17 +139,28 @@ class PseudoInverseController(BaseController):
     def setup_solver(self):
         self.setup_problem_functions()
 
-    def _skill(self):
-        if self._compiled is None:
-            if getattr(self, "_cubin", None) is None:
-                raise RuntimeError("call setup_problem_functions() / setup_solver() before solve()")
-            self._compiled = runtime.CompiledSkill(self._cubin, self.kernel_meta,
-                                                   n_slack=self.skill_spec.n_slack_var)
-        return self._compiled
+    def _skill(self, device=None):
+        """The cubin loaded on `device` (default: runtime.current_device()); one handle per device,
+        created on first use, so a batch always runs on the device its tensors live on."""
+        if getattr(self, "_cubin", None) is None:
+            raise RuntimeError("call setup_problem_functions() / setup_solver() before solve()")
+        if not isinstance(self._compiled, dict):
+            first = self._compiled
+            self._compiled = {} if first is None else {first.device: first}
+        dev = runtime.current_device() if device is None else int(device)
+        if dev not in self._compiled:
+            self._compiled[dev] = runtime.CompiledSkill(self._cubin, self.kernel_meta,
+                                                        n_slack=self.skill_spec.n_slack_var, device=dev)
+        return self._compiled[dev]
 
     # ---- step --------------------------------------------------------------------------------------
-    def solve_batch(self, time_var, robot_var, virtual_var=None, input_var=None, out=None):
+    def solve_batch(self, time_var, robot_var, virtual_var=None, input_var=None, out=None, devices=None):
         """Controller step for N instances.
+
+        devices (host arrays only): None = one GPU; "all", a count or a list of CUDA ordinals = the
+        batch is cut into contiguous shards, one per device, each solved in place on its device
+        (no collective, no repacking), results gathered in the returned host arrays — the sharded
+        solve of BASELINE.json configs[4].  Bit-identical to the single-device call.
 
         robot_var (n_robot, N), virtual_var (n_virtual, N), input_var (n_input, N): float64,
         coordinate-major; torch CUDA tensors (zero-copy, asynchronous on the current stream) or
@@ -156,23 +168,35 @@ class PseudoInverseController(BaseController):
         Returns (robot_vel (n_robot, N), virtual_vel (n_virtual, N) | None, mode (N,) int32) with
         mode = index into `activation_map` (0 when the skill has no sets), -1 = no admissible
         mode (velocities are zero)."""
-        skill = self._skill()
         spec = self.skill_spec
         nq, nx, ny = spec.n_robot_var, self._nx, self._ny
         b = Batch(nq, nx, ny, time_var, robot_var, virtual_var, input_var if ny else None)
+        devs = resolve_devices(devices)
+        if devs is not None and b.on_device:
+            raise ValueError("devices= applies to host arrays; CUDA tensors run on the device they live on")
+        skill = self._skill(b.device_index if devs is None else devs[0])
         if out is None:
             qdot = b.empty(nq)
             xdot = b.empty(nx) if nx else None
             mode = b.empty(0, "i32")
         else:
             qdot, xdot, mode = out
+            if qdot is None or (nx and xdot is None):
+                raise runtime.ClikError("out=(robot_vel, virtual_vel, mode): the velocity buffers are required")
+        qdp, xdp = b.out_ptr(qdot, nq, "f64", "out[0] (robot_vel)"), \
+            (b.out_ptr(xdot, nx, "f64", "out[1] (virtual_vel)") if nx else None)
+        mdp = b.out_ptr(mode, 0, "i32", "out[2] (mode)")
         lib = runtime.load_library()
         if b.on_device:
             runtime.check(lib.clik_pinv_step(skill.handle, b.N, b.tp, b.t_stride, b.qp, b.xp, b.yp,
-                                             b.ptr(qdot), b.ptr(xdot), b.ptr(mode), b.stream()))
+                                             qdp, xdp, mdp, b.stream()))
+        elif devs is not None and len(devs) > 1:
+            skills = [self._skill(d) for d in devs]
+            runtime.check(lib.clik_pinv_step_host_multi(skill_handle_array(skills), len(skills), b.N, b.tp,
+                                                        b.t_stride, b.qp, b.xp, b.yp, qdp, xdp, mdp))
         else:
             runtime.check(lib.clik_pinv_step_host(skill.handle, b.N, b.tp, b.t_stride, b.qp, b.xp,
-                                                  b.yp, b.ptr(qdot), b.ptr(xdot), b.ptr(mode)))
+                                                  b.yp, qdp, xdp, mdp))
         return qdot, xdot, mode
 
     def rollout_batch(self, time_var0, robot_var, steps, dt, virtual_var=None, input_var=None,
@@ -183,12 +207,12 @@ class PseudoInverseController(BaseController):
         CUDA tensors (n, N) and are UPDATED IN PLACE.  Returns a dict with the last command
         (`robot_vel`, `virtual_vel`), its `mode`, and `n_failed` (steps with no admissible mode)."""
         import ctypes
-        skill = self._skill()
         spec = self.skill_spec
         nq, nx, ny = spec.n_robot_var, self._nx, self._ny
         b = Batch(nq, nx, ny, time_var0, robot_var, virtual_var, input_var if ny else None)
         if not b.on_device:
             raise ValueError("rollout_batch needs CUDA tensors (state is updated in place on the device)")
+        skill = self._skill(b.device_index)
         if nx and virtual_var is None:
             raise ValueError("the skill has a virtual_var: pass its initial value")
         qdot, xdot = b.empty(nq), (b.empty(nx) if nx else None)

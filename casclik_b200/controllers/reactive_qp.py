@@ -20,7 +20,7 @@ import numpy as np
 from .. import build, runtime
 from .. import sym as cs
 from ..codegen import QpProgram, emit_skill
-from .base_controller import BaseController, Batch, as_vector, dm_column
+from .base_controller import BaseController, Batch, as_vector, dm_column, resolve_devices, skill_handle_array
 from .qp_solver import ConicSolver
 
 
@@ -176,7 +176,7 @@ class ReactiveQPController(BaseController):
         self.Blb_func = cs.Function("Blb_expr", ins, [cs.MX(cs.vertcat(*prog.lb))], names, ["Blb"])
         self.Bub_func = cs.Function("Bub_expr", ins, [cs.MX(cs.vertcat(*prog.ub))], names, ["Bub"])
         if load:
-            self._compiled = runtime.CompiledSkill(cubin, meta, n_slack=self.skill_spec.n_slack_var)
+            self._skill()
 
     def setup_solver(self):
         """`self.solver`: the conic-call object (reference :248-260).  Either order of
@@ -186,13 +186,18 @@ class ReactiveQPController(BaseController):
         if self._cubin is None:
             self.setup_problem_functions()
 
-    def _skill(self):
-        if self._compiled is None:
-            if self._cubin is None:
-                raise RuntimeError("call setup_problem_functions() / setup_solver() before solve()")
-            self._compiled = runtime.CompiledSkill(self._cubin, self.kernel_meta,
-                                                   n_slack=self.skill_spec.n_slack_var)
-        return self._compiled
+    def _skill(self, device=None):
+        """The cubin loaded on `device` (default: runtime.current_device()); one handle per device."""
+        if self._cubin is None:
+            raise RuntimeError("call setup_problem_functions() / setup_solver() before solve()")
+        if not isinstance(self._compiled, dict):
+            first = self._compiled
+            self._compiled = {} if first is None else {first.device: first}
+        dev = runtime.current_device() if device is None else int(device)
+        if dev not in self._compiled:
+            self._compiled[dev] = runtime.CompiledSkill(self._cubin, self.kernel_meta,
+                                                        n_slack=self.skill_spec.n_slack_var, device=dev)
+        return self._compiled[dev]
 
     # ---- initial problem (virtual + slack with robot velocity fixed), reference :300-459 ---------------
     def setup_initial_problem_solver(self):
@@ -209,23 +214,32 @@ class ReactiveQPController(BaseController):
 
     # ---- step --------------------------------------------------------------------------------------
     def solve_batch(self, time_var, robot_var, virtual_var=None, input_var=None, warmstart=None,
-                    out=None, max_iter=None, warm_active=None):
+                    out=None, max_iter=None, warm_active=None, devices=None):
         """QP controller step for N instances (same layout rules as
         PseudoInverseController.solve_batch).  warmstart: optional (nx, N) primal guess;
         warm_active: optional (2, N) int32 working-set guess in the format of the returned `active`
         (e.g. the previous step's).  Either only shortens the active-set iteration.
+        devices: as in PseudoInverseController.solve_batch (host arrays sharded over several GPUs).
         Returns (sol (nx, N), status (N,) int32, active (2, N) int32 bit masks [upper; lower]);
         rows of `sol` are [robot vel; virtual vel; slack]."""
-        skill = self._skill()
         spec = self.skill_spec
         b = Batch(spec.n_robot_var, self._nxv, self._ny, time_var, robot_var, virtual_var,
                   input_var if self._ny else None)
+        devs = resolve_devices(devices)
+        if devs is not None and b.on_device:
+            raise ValueError("devices= applies to host arrays; CUDA tensors run on the device they live on")
+        skill = self._skill(b.device_index if devs is None else devs[0])
         if out is None:
             sol = b.empty(self._qn)
             status = b.empty(0, "i32")
             active = b.empty(2, "i32")
         else:
             sol, status, active = out
+            if sol is None:
+                raise runtime.ClikError("out=(sol, status, active): the solution buffer is required")
+        solp = b.out_ptr(sol, self._qn, "f64", "out[0] (sol)")
+        stp = b.out_ptr(status, 0, "i32", "out[1] (status)")
+        acp = b.out_ptr(active, 2, "i32", "out[2] (active)")
         x0p = None
         if warmstart is not None:
             if b.on_device:
@@ -242,12 +256,14 @@ class ReactiveQPController(BaseController):
         lib = runtime.load_library()
         if b.on_device:
             runtime.check(lib.clik_qp_step(skill.handle, b.N, b.tp, b.t_stride, b.qp, b.xp, b.yp,
-                                           x0p, a0p, b.ptr(sol), b.ptr(status), b.ptr(active), mi,
-                                           b.stream()))
+                                           x0p, a0p, solp, stp, acp, mi, b.stream()))
+        elif devs is not None and len(devs) > 1:
+            skills = [self._skill(d) for d in devs]
+            runtime.check(lib.clik_qp_step_host_multi(skill_handle_array(skills), len(skills), b.N, b.tp,
+                                                      b.t_stride, b.qp, b.xp, b.yp, x0p, a0p, solp, stp, acp, mi))
         else:
             runtime.check(lib.clik_qp_step_host(skill.handle, b.N, b.tp, b.t_stride, b.qp, b.xp,
-                                                b.yp, x0p, a0p, b.ptr(sol), b.ptr(status),
-                                                b.ptr(active), mi))
+                                                b.yp, x0p, a0p, solp, stp, acp, mi))
         return sol, status, active
 
     def rollout_batch(self, time_var0, robot_var, steps, dt, virtual_var=None, input_var=None,
@@ -256,12 +272,12 @@ class ReactiveQPController(BaseController):
         robot_var / virtual_var (torch CUDA, (n, N)) are UPDATED IN PLACE.  Returns a dict with the
         last QP solution `sol` (nx, N) and `n_failed` (steps whose QP was not solved: zero velocity)."""
         import ctypes
-        skill = self._skill()
         spec = self.skill_spec
         b = Batch(spec.n_robot_var, self._nxv, self._ny, time_var0, robot_var, virtual_var,
                   input_var if self._ny else None)
         if not b.on_device:
             raise ValueError("rollout_batch needs CUDA tensors (state is updated in place on the device)")
+        skill = self._skill(b.device_index)
         if self._nxv and virtual_var is None:
             raise ValueError("the skill has a virtual_var: pass its initial value")
         sol, failed = b.empty(self._qn), b.empty(0, "i32")

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstdint>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -45,6 +46,21 @@ clik_status fail(clik_status code, const char* fmt, ...) {
                                                                                : CLIK_ERR_CUDA, \
                   "%s failed: %s", #call, cudaGetErrorString(e_));                            \
   } while (0)
+
+// Every entry point runs on the skill's device and leaves the caller's current device as it found it
+// (the caller may be torch, with its own idea of the current device).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    if (prev != dev) err = cudaSetDevice(dev); else prev = -1;   // nothing to restore
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(dev)       \
+  DeviceGuard guard_(dev);   \
+  CK(guard_.err)
 
 struct KernelInfo {
   cudaKernel_t kernel = nullptr;
@@ -248,24 +264,26 @@ clik_status for_row_runs(int rows, unsigned mask, Copy copy) {
   return CLIK_OK;
 }
 
+// Instances [lo, lo + cnt) of a host batch whose rows are N apart (lo = 0, cnt = N: the whole batch).
 template <class Launch>
-clik_status run_host_pipeline(clik_skill* s, int64_t N, std::vector<Field>& f, Launch launch) {
+clik_status run_host_pipeline(clik_skill* s, int64_t N, int64_t lo, int64_t cnt, std::vector<Field>& f,
+                              Launch launch) {
   std::lock_guard<std::mutex> lock(s->mu);
-  CK(cudaSetDevice(s->desc.device));
-  const int64_t chunk = std::min<int64_t>(N, host_chunk());
+  ON_DEVICE(s->desc.device);
+  const int64_t chunk = std::min<int64_t>(cnt, host_chunk());
   size_t bytes = 0;
   for (auto& fl : f) {
     fl.dev_off = bytes;
     bytes += (((size_t)fl.rows * chunk * fl.elem) + 255) & ~(size_t)255;
   }
-  const int nslots = (int)std::min<int64_t>(NSLOTS, (N + chunk - 1) / chunk);
+  const int nslots = (int)std::min<int64_t>(NSLOTS, (cnt + chunk - 1) / chunk);
   for (int slot = 0; slot < nslots; ++slot) {
     clik_status st = ensure_scratch(s, slot, bytes);
     if (st != CLIK_OK) return st;
   }
   int slot = 0;
-  for (int64_t i0 = 0; i0 < N; i0 += chunk, slot = (slot + 1) % nslots) {
-    const int64_t c = std::min<int64_t>(chunk, N - i0);
+  for (int64_t i0 = lo; i0 < lo + cnt; i0 += chunk, slot = (slot + 1) % nslots) {
+    const int64_t c = std::min<int64_t>(chunk, lo + cnt - i0);
     cudaStream_t st = s->scratch.stream[slot];
     char* base = (char*)s->scratch.dev[slot];
     for (auto& fl : f) {
@@ -319,7 +337,7 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
                 CLIK_ABI_VERSION);
   if (desc->n_robot <= 0) return fail(CLIK_ERR_INVALID, "n_robot must be positive");
   *out = nullptr;
-  CK(cudaSetDevice(desc->device));
+  ON_DEVICE(desc->device);
   clik_skill* s = new clik_skill();
   s->desc = *desc;
   cudaError_t e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, desc->device);
@@ -385,7 +403,7 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
 
 void clik_skill_free(clik_skill* s) {
   if (!s) return;
-  cudaSetDevice(s->desc.device);
+  DeviceGuard guard(s->desc.device);
   for (int i = 0; i < NSLOTS; ++i) {
     if (s->scratch.dev[i]) cudaFree(s->scratch.dev[i]);
     if (s->scratch.stream[i]) cudaStreamDestroy(s->scratch.stream[i]);
@@ -406,20 +424,21 @@ clik_status clik_skill_launch_info(const clik_skill* s, int32_t which, int32_t* 
   return CLIK_OK;
 }
 
-clik_status clik_pinv_step(const clik_skill* s, int64_t N, const double* t, int32_t t_stride,
-                           const double* q, const double* x, const double* y, double* qdot,
-                           double* xdot, int32_t* mode, void* stream) {
+clik_status clik_pinv_step_ld(const clik_skill* s, int64_t N, int64_t ld, const double* t, int32_t t_stride,
+                              const double* q, const double* x, const double* y, double* qdot,
+                              double* xdot, int32_t* mode, void* stream) {
   clik_status st = check_common(s, N, t, q, x, y);
   if (st != CLIK_OK || N == 0) return st;
+  if (ld < N) return fail(CLIK_ERR_INVALID, "row stride ld (%lld) < N (%lld)", (long long)ld, (long long)N);
   if (!s->pinv.kernel) return fail(CLIK_ERR_INVALID, "skill was built without the pinv kernel");
   if (!qdot) return fail(CLIK_ERR_INVALID, "qdot is required");
   if (s->desc.n_virtual > 0 && !xdot) return fail(CLIK_ERR_INVALID, "xdot is required");
-  CK(cudaSetDevice(s->desc.device));
-  long long n = N;
+  ON_DEVICE(s->desc.device);
+  long long n = N, l = ld;
   int ts = t_stride ? 1 : 0;
-  void* args[] = {&n, &t, &ts, &q, &x, &y, &qdot, &xdot, &mode};
-  // bulk async copies need 16-byte aligned row segments: even N and aligned bases
-  const bool tma_ok = s->use_tma && s->pinv_tma.kernel && (N % 2 == 0) && aligned16(t) && aligned16(q) &&
+  void* args[] = {&n, &l, &t, &ts, &q, &x, &y, &qdot, &xdot, &mode};
+  // bulk async copies need 16-byte aligned row segments: even stride and aligned bases
+  const bool tma_ok = s->use_tma && s->pinv_tma.kernel && (ld % 2 == 0) && aligned16(t) && aligned16(q) &&
                       aligned16(x) && aligned16(y);
   if (tma_ok) {
     CK(cudaLaunchKernel((const void*)s->pinv_tma.kernel, dim3(balanced_grid(s->pinv_tma, N)),
@@ -431,6 +450,12 @@ clik_status clik_pinv_step(const clik_skill* s, int64_t N, const double* t, int3
   return CLIK_OK;
 }
 
+clik_status clik_pinv_step(const clik_skill* s, int64_t N, const double* t, int32_t t_stride,
+                           const double* q, const double* x, const double* y, double* qdot,
+                           double* xdot, int32_t* mode, void* stream) {
+  return clik_pinv_step_ld(s, N, N, t, t_stride, q, x, y, qdot, xdot, mode, stream);
+}
+
 clik_status clik_pinv_rollout(const clik_skill* s, int64_t N, int32_t steps, double dt, const double* t0,
                               int32_t t_stride, double* q, double* x, const double* y,
                               double max_robot_speed, double max_virtual_speed, double* qdot_last,
@@ -439,29 +464,30 @@ clik_status clik_pinv_rollout(const clik_skill* s, int64_t N, int32_t steps, dou
   if (st != CLIK_OK || N == 0) return st;
   if (!s->pinv_rollout.kernel) return fail(CLIK_ERR_INVALID, "skill was built without the rollout kernel");
   if (steps < 0) return fail(CLIK_ERR_INVALID, "steps < 0");
-  CK(cudaSetDevice(s->desc.device));
-  long long n = N;
+  ON_DEVICE(s->desc.device);
+  long long n = N, l = N;
   int ts = t_stride ? 1 : 0, k = steps;
-  void* args[] = {&n, &k, &dt, &t0, &ts, &q, &x, &y, &max_robot_speed, &max_virtual_speed,
+  void* args[] = {&n, &l, &k, &dt, &t0, &ts, &q, &x, &y, &max_robot_speed, &max_virtual_speed,
                   &qdot_last, &xdot_last, &mode_last, &n_failed};
   CK(cudaLaunchKernel((const void*)s->pinv_rollout.kernel, dim3(grid_for(s->pinv_rollout, N)),
                       dim3(s->pinv_rollout.block), args, 0, (cudaStream_t)stream));
   return CLIK_OK;
 }
 
-clik_status clik_qp_step(const clik_skill* s, int64_t N, const double* t, int32_t t_stride,
-                         const double* q, const double* x, const double* y, const double* x0,
-                         const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
-                         int32_t max_iter, void* stream) {
+clik_status clik_qp_step_ld(const clik_skill* s, int64_t N, int64_t ld, const double* t, int32_t t_stride,
+                            const double* q, const double* x, const double* y, const double* x0,
+                            const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
+                            int32_t max_iter, void* stream) {
   clik_status st = check_common(s, N, t, q, x, y);
   if (st != CLIK_OK || N == 0) return st;
+  if (ld < N) return fail(CLIK_ERR_INVALID, "row stride ld (%lld) < N (%lld)", (long long)ld, (long long)N);
   if (!s->qp.kernel) return fail(CLIK_ERR_INVALID, "skill was built without the QP kernel");
   if (!sol) return fail(CLIK_ERR_INVALID, "sol is required");
-  CK(cudaSetDevice(s->desc.device));
-  long long n = N;
+  ON_DEVICE(s->desc.device);
+  long long n = N, l = ld;
   int ts = t_stride ? 1 : 0;
   int mi = max_iter > 0 ? max_iter : 10 * (s->desc.qp_n + s->desc.qp_m);
-  void* args[] = {&n, &t, &ts, &q, &x, &y, &x0, &active0, &sol, &status, &active, &mi};
+  void* args[] = {&n, &l, &t, &ts, &q, &x, &y, &x0, &active0, &sol, &status, &active, &mi};
   if (s->qp_fast.kernel && s->qp_tail.kernel && s->qp_split && status != nullptr) {
     // two launches: the working-set prediction for every instance (no Goldfarb-Idnani code in that
     // kernel: ~160 registers instead of 255 + spills), then the full solver for the few instances the
@@ -478,6 +504,13 @@ clik_status clik_qp_step(const clik_skill* s, int64_t N, const double* t, int32_
   return CLIK_OK;
 }
 
+clik_status clik_qp_step(const clik_skill* s, int64_t N, const double* t, int32_t t_stride,
+                         const double* q, const double* x, const double* y, const double* x0,
+                         const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
+                         int32_t max_iter, void* stream) {
+  return clik_qp_step_ld(s, N, N, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter, stream);
+}
+
 clik_status clik_qp_rollout(const clik_skill* s, int64_t N, int32_t steps, double dt, const double* t0,
                             int32_t t_stride, double* q, double* x, const double* y,
                             double max_robot_speed, double max_virtual_speed, double* sol_last,
@@ -486,11 +519,11 @@ clik_status clik_qp_rollout(const clik_skill* s, int64_t N, int32_t steps, doubl
   if (st != CLIK_OK || N == 0) return st;
   if (!s->qp_rollout.kernel) return fail(CLIK_ERR_INVALID, "skill was built without the QP rollout kernel");
   if (steps < 0) return fail(CLIK_ERR_INVALID, "steps < 0");
-  CK(cudaSetDevice(s->desc.device));
-  long long n = N;
+  ON_DEVICE(s->desc.device);
+  long long n = N, l = N;
   int ts = t_stride ? 1 : 0, k = steps;
   int mi = max_iter > 0 ? max_iter : 10 * (s->desc.qp_n + s->desc.qp_m);
-  void* args[] = {&n, &k, &dt, &t0, &ts, &q, &x, &y, &max_robot_speed, &max_virtual_speed,
+  void* args[] = {&n, &l, &k, &dt, &t0, &ts, &q, &x, &y, &max_robot_speed, &max_virtual_speed,
                   &sol_last, &n_failed, &mi};
   CK(cudaLaunchKernel((const void*)s->qp_rollout.kernel, dim3(grid_for(s->qp_rollout, N)),
                       dim3(s->qp_rollout.block), args, 0, (cudaStream_t)stream));
@@ -506,7 +539,7 @@ clik_status clik_qp_dense(int32_t device, int64_t N, int32_t nx, int32_t m, cons
     return fail(CLIK_ERR_INVALID, "clik_qp_dense supports nx <= %d, m <= %d", DENSE_NX, DENSE_M);
   if (N == 0) return CLIK_OK;
   if (!h || (m > 0 && (!A || !lb || !ub)) || !sol) return fail(CLIK_ERR_INVALID, "NULL argument");
-  CK(cudaSetDevice(device));
+  ON_DEVICE(device);
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int block = 64;
@@ -518,25 +551,29 @@ clik_status clik_qp_dense(int32_t device, int64_t N, int32_t nx, int32_t m, cons
   return CLIK_OK;
 }
 
-clik_status clik_pinv_step_host(const clik_skill* cs, int64_t N, const double* t, int32_t t_stride,
-                                const double* q, const double* x, const double* y, double* qdot,
-                                double* xdot, int32_t* mode) {
-  clik_skill* s = const_cast<clik_skill*>(cs);
-  clik_status st = check_common(s, N, t, q, x, y);
-  if (st != CLIK_OK || N == 0) return st;
-  if (!qdot) return fail(CLIK_ERR_INVALID, "qdot is required");
+}  // extern "C"
+
+namespace {
+
+// ---- host-buffer entry points: instances [lo, lo + cnt) of a host batch of N ------------------------
+clik_status pinv_host_range(clik_skill* s, int64_t N, int64_t lo, int64_t cnt, const double* t,
+                            int32_t t_stride, const double* q, const double* x, const double* y,
+                            double* qdot, double* xdot, int32_t* mode) {
   const clik_skill_desc& d = s->desc;
+  if (cnt <= 0) return CLIK_OK;
   if (zero_copy_enabled()) {
     const void *dt, *dq, *dx, *dy, *dqd, *dxd, *dm;
-    CK(cudaSetDevice(d.device));
+    ON_DEVICE(d.device);
     if (device_alias(t, &dt) && device_alias(q, &dq) && device_alias(d.n_virtual ? x : nullptr, &dx) &&
         device_alias(d.n_input ? y : nullptr, &dy) && device_alias(qdot, &dqd) &&
         device_alias(d.n_virtual ? xdot : nullptr, &dxd) && device_alias(mode, &dm)) {
       std::lock_guard<std::mutex> lock(s->mu);
       clik_status zs = ensure_scratch(s, 0, 256);
       if (zs != CLIK_OK) return zs;
-      zs = clik_pinv_step(s, N, (const double*)dt, t_stride, (const double*)dq, (const double*)dx,
-                          (const double*)dy, (double*)dqd, (double*)dxd, (int32_t*)dm, s->scratch.stream[0]);
+      auto off = [lo](const void* p) { return p ? (const double*)p + lo : nullptr; };
+      zs = clik_pinv_step_ld(s, cnt, N, t_stride ? off(dt) : (const double*)dt, t_stride, off(dq), off(dx),
+                             off(dy), (double*)off(dqd), (double*)off(dxd),
+                             dm ? (int32_t*)dm + lo : nullptr, s->scratch.stream[0]);
       if (zs != CLIK_OK) return zs;
       CK(cudaStreamSynchronize(s->scratch.stream[0]));
       return CLIK_OK;
@@ -554,7 +591,7 @@ clik_status clik_pinv_step_host(const clik_skill* cs, int64_t N, const double* t
   f.push_back({nullptr, qdot, d.n_robot, 8, 1, 0});
   f.push_back({nullptr, d.n_virtual ? xdot : nullptr, d.n_virtual, 8, 1, 0});
   f.push_back({nullptr, mode, 1, 4, 1, 0});
-  return run_host_pipeline(s, N, f, [&](char* base, int64_t c, cudaStream_t stream) {
+  return run_host_pipeline(s, N, lo, cnt, f, [&](char* base, int64_t c, cudaStream_t stream) {
     return clik_pinv_step(s, c, (const double*)(base + f[0].dev_off), t_stride,
                           (const double*)(base + f[1].dev_off),
                           d.n_virtual ? (const double*)(base + f[2].dev_off) : nullptr,
@@ -565,27 +602,26 @@ clik_status clik_pinv_step_host(const clik_skill* cs, int64_t N, const double* t
   });
 }
 
-clik_status clik_qp_step_host(const clik_skill* cs, int64_t N, const double* t, int32_t t_stride,
-                              const double* q, const double* x, const double* y, const double* x0,
-                              const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
-                              int32_t max_iter) {
-  clik_skill* s = const_cast<clik_skill*>(cs);
-  clik_status st = check_common(s, N, t, q, x, y);
-  if (st != CLIK_OK || N == 0) return st;
-  if (!sol) return fail(CLIK_ERR_INVALID, "sol is required");
+clik_status qp_host_range(clik_skill* s, int64_t N, int64_t lo, int64_t cnt, const double* t, int32_t t_stride,
+                          const double* q, const double* x, const double* y, const double* x0,
+                          const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
+                          int32_t max_iter) {
   const clik_skill_desc& d = s->desc;
+  if (cnt <= 0) return CLIK_OK;
   if (zero_copy_enabled()) {
     const void *dt, *dq, *dx, *dy, *dx0, *da0, *dsol, *dst, *dact;
-    CK(cudaSetDevice(d.device));
+    ON_DEVICE(d.device);
     if (device_alias(t, &dt) && device_alias(q, &dq) && device_alias(d.n_virtual ? x : nullptr, &dx) &&
         device_alias(d.n_input ? y : nullptr, &dy) && device_alias(x0, &dx0) && device_alias(active0, &da0) &&
         device_alias(sol, &dsol) && device_alias(status, &dst) && device_alias(active, &dact)) {
       std::lock_guard<std::mutex> lock(s->mu);
       clik_status zs = ensure_scratch(s, 0, 256);
       if (zs != CLIK_OK) return zs;
-      zs = clik_qp_step(s, N, (const double*)dt, t_stride, (const double*)dq, (const double*)dx,
-                        (const double*)dy, (const double*)dx0, (const uint32_t*)da0, (double*)dsol,
-                        (int32_t*)dst, (uint32_t*)dact, max_iter, s->scratch.stream[0]);
+      auto off = [lo](const void* p) { return p ? (const double*)p + lo : nullptr; };
+      zs = clik_qp_step_ld(s, cnt, N, t_stride ? off(dt) : (const double*)dt, t_stride, off(dq), off(dx), off(dy),
+                           off(dx0), da0 ? (const uint32_t*)da0 + lo : nullptr, (double*)off(dsol),
+                           dst ? (int32_t*)dst + lo : nullptr, dact ? (uint32_t*)dact + lo : nullptr, max_iter,
+                           s->scratch.stream[0]);
       if (zs != CLIK_OK) return zs;
       CK(cudaStreamSynchronize(s->scratch.stream[0]));
       return CLIK_OK;
@@ -605,7 +641,7 @@ clik_status clik_qp_step_host(const clik_skill* cs, int64_t N, const double* t, 
   f.push_back({nullptr, status, 1, 4, 1, 0});
   f.push_back({nullptr, active, 2, 4, 1, 0});
   f.push_back({active0, nullptr, 2, 4, 1, 0});
-  return run_host_pipeline(s, N, f, [&](char* base, int64_t c, cudaStream_t stream) {
+  return run_host_pipeline(s, N, lo, cnt, f, [&](char* base, int64_t c, cudaStream_t stream) {
     return clik_qp_step(s, c, (const double*)(base + f[0].dev_off), t_stride,
                         (const double*)(base + f[1].dev_off),
                         d.n_virtual ? (const double*)(base + f[2].dev_off) : nullptr,
@@ -618,9 +654,76 @@ clik_status clik_qp_step_host(const clik_skill* cs, int64_t N, const double* t, 
   });
 }
 
+// Contiguous shards of one host batch, one per skill handle (= per device), each on its own host
+// thread; no exchange between devices (instances are independent), results land in the caller's arrays.
+template <class Run>
+clik_status run_sharded(const clik_skill* const* skills, int32_t n_skills, int64_t N, Run run) {
+  if (!skills || n_skills < 1) return fail(CLIK_ERR_INVALID, "no skill handles");
+  for (int k = 0; k < n_skills; ++k)
+    if (!skills[k]) return fail(CLIK_ERR_INVALID, "skill handle %d is NULL", k);
+  if (n_skills == 1 || N < n_skills) return run(const_cast<clik_skill*>(skills[0]), (int64_t)0, N);
+  std::vector<clik_status> st(n_skills, CLIK_OK);
+  std::vector<std::string> msg(n_skills);
+  std::vector<std::thread> th;
+  const int64_t base = N / n_skills, rem = N % n_skills;
+  for (int k = 0; k < n_skills; ++k) {
+    const int64_t lo = k * base + std::min<int64_t>(k, rem), cnt = base + (k < rem ? 1 : 0);
+    th.emplace_back([&, k, lo, cnt] {
+      st[k] = run(const_cast<clik_skill*>(skills[k]), lo, cnt);
+      if (st[k] != CLIK_OK) msg[k] = g_err;      // g_err is per thread: carry the text back
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int k = 0; k < n_skills; ++k)
+    if (st[k] != CLIK_OK) return fail(st[k], "shard %d (device %d): %s", k, skills[k]->desc.device, msg[k].c_str());
+  return CLIK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+clik_status clik_pinv_step_host(const clik_skill* cs, int64_t N, const double* t, int32_t t_stride,
+                                const double* q, const double* x, const double* y, double* qdot,
+                                double* xdot, int32_t* mode) {
+  return clik_pinv_step_host_multi(&cs, 1, N, t, t_stride, q, x, y, qdot, xdot, mode);
+}
+
+clik_status clik_pinv_step_host_multi(const clik_skill* const* skills, int32_t n_skills, int64_t N,
+                                      const double* t, int32_t t_stride, const double* q, const double* x,
+                                      const double* y, double* qdot, double* xdot, int32_t* mode) {
+  if (!skills || n_skills < 1 || !skills[0]) return fail(CLIK_ERR_INVALID, "no skill handles");
+  clik_status st = check_common(skills[0], N, t, q, x, y);
+  if (st != CLIK_OK || N == 0) return st;
+  if (!qdot) return fail(CLIK_ERR_INVALID, "qdot is required");
+  return run_sharded(skills, n_skills, N, [&](clik_skill* s, int64_t lo, int64_t cnt) {
+    return pinv_host_range(s, N, lo, cnt, t, t_stride, q, x, y, qdot, xdot, mode);
+  });
+}
+
+clik_status clik_qp_step_host(const clik_skill* cs, int64_t N, const double* t, int32_t t_stride,
+                              const double* q, const double* x, const double* y, const double* x0,
+                              const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
+                              int32_t max_iter) {
+  return clik_qp_step_host_multi(&cs, 1, N, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);
+}
+
+clik_status clik_qp_step_host_multi(const clik_skill* const* skills, int32_t n_skills, int64_t N,
+                                    const double* t, int32_t t_stride, const double* q, const double* x,
+                                    const double* y, const double* x0, const uint32_t* active0, double* sol,
+                                    int32_t* status, uint32_t* active, int32_t max_iter) {
+  if (!skills || n_skills < 1 || !skills[0]) return fail(CLIK_ERR_INVALID, "no skill handles");
+  clik_status st = check_common(skills[0], N, t, q, x, y);
+  if (st != CLIK_OK || N == 0) return st;
+  if (!sol) return fail(CLIK_ERR_INVALID, "sol is required");
+  return run_sharded(skills, n_skills, N, [&](clik_skill* s, int64_t lo, int64_t cnt) {
+    return qp_host_range(s, N, lo, cnt, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);
+  });
+}
+
 clik_status clik_measure_fp64_peak(int32_t device, int32_t iters, double* tflops) {
   if (!tflops || iters <= 0) return fail(CLIK_ERR_INVALID, "bad argument");
-  CK(cudaSetDevice(device));
+  ON_DEVICE(device);
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int block = 256, grid = sms * 8;
@@ -649,7 +752,7 @@ clik_status clik_measure_fp64_peak(int32_t device, int32_t iters, double* tflops
 
 clik_status clik_flush_l2(int32_t device, void* stream) {
   if (device < 0 || device >= 64) return fail(CLIK_ERR_INVALID, "bad device");
-  CK(cudaSetDevice(device));
+  ON_DEVICE(device);
   {
     std::lock_guard<std::mutex> lock(g_flush_mu);
     if (!g_flush_buf[device]) CK(cudaMalloc(&g_flush_buf[device], FLUSH_BYTES));

@@ -332,10 +332,12 @@ template <class S, unsigned MASK, int C, class Stack, bool PRE> struct StaticMod
           using S1 = typename Concat<Stack, RC>::type;
           if constexpr (kind == KIND_EQ) {
             // :322-326 and, because the reference's next chain starts with a new `if`, :382-396
+            // (an empty stack means nothing has contributed yet: v is still zero, so the first
+            // contribution is assigned — "0 + w" would cost one fp64 add per coordinate)
             if constexpr (S::FUSE_FIRST_EQ && !PRE) {
               first_equality_twice<S, RC>(d.J, b, w);
 #pragma unroll
-              for (int j = 0; j < S::NS; ++j) v[j] += w[j];
+              for (int j = 0; j < S::NS; ++j) v[j] = w[j];
             } else {
               if constexpr (PRE) {
 #pragma unroll
@@ -344,7 +346,7 @@ template <class S, unsigned MASK, int C, class Stack, bool PRE> struct StaticMod
                 pinv_times<S, RC>(d.J, b, w);
               }
 #pragma unroll
-              for (int j = 0; j < S::NS; ++j) v[j] += w[j];
+              for (int j = 0; j < S::NS; ++j) v[j] = w[j];
               nullspace_apply<S, S1>(d.J, d.rmask, w);
 #pragma unroll
               for (int j = 0; j < S::NS; ++j) v[j] += w[j];
@@ -358,7 +360,7 @@ template <class S, unsigned MASK, int C, class Stack, bool PRE> struct StaticMod
               pinv_times<S, RC>(d.J, b, w);                              // :331-335
             }
 #pragma unroll
-            for (int j = 0; j < S::NS; ++j) v[j] += w[j];
+            for (int j = 0; j < S::NS; ++j) v[j] = w[j];
             StaticMode<S, MASK, C + 1, S1, PRE>::run(d, tw, v);
           }
         } else {
@@ -762,33 +764,36 @@ __device__ __forceinline__ int solve_instance(const double tv, const double (&qv
 }
 
 template <class S>
-__device__ __forceinline__ void store_instance(long long N, long long i, const double (&v)[S::NS],
+__device__ __forceinline__ void store_instance(long long ld, long long i, const double (&v)[S::NS],
                                                int accepted, double* __restrict__ qdot,
                                                double* __restrict__ xdot, int* __restrict__ mode) {
 #pragma unroll
-  for (int j = 0; j < S::NQ; ++j) __stcs(qdot + (long long)j * N + i, v[j]);
+  for (int j = 0; j < S::NQ; ++j) __stcs(qdot + (long long)j * ld + i, v[j]);
 #pragma unroll
-  for (int j = 0; j < S::NX; ++j) __stcs(xdot + (long long)j * N + i, v[S::NQ + j]);
+  for (int j = 0; j < S::NX; ++j) __stcs(xdot + (long long)j * ld + i, v[S::NQ + j]);
   if (mode != nullptr) __stcs(mode + i, accepted);
 }
 
-// Plain driver.  Structure-of-arrays batch: q[j*N + i] is coordinate j of instance i (same for
-// x, y, outputs), so consecutive threads touch consecutive addresses.  t has stride t_stride
+// Plain driver.  Structure-of-arrays batch: q[j*ld + i] is coordinate j of instance i (same for
+// x, y, outputs), so consecutive threads touch consecutive addresses; N instances are processed and
+// ld >= N is the row stride (ld = N for a whole batch; ld = size of the whole batch when the call
+// covers one shard [lo, lo + N) of it, with every pointer advanced by lo: how one host batch is split
+// over several GPUs without repacking).  t has stride t_stride
 // (0 = one shared time).  mode[i] = index into the activation map of the accepted mode, -1 (and
 // zero velocity) if none.  Used when the TMA driver's alignment conditions do not hold.
 template <class S>
-__device__ __forceinline__ void load_instance(long long N, long long i, const double* __restrict__ t,
+__device__ __forceinline__ void load_instance(long long ld, long long i, const double* __restrict__ t,
                                               int t_stride, const double* __restrict__ q,
                                               const double* __restrict__ x, const double* __restrict__ y,
                                               double& tv, double (&qv)[Max<S::NQ, 1>::v],
                                               double (&xv)[Max<S::NX, 1>::v], double (&yv)[Max<S::NY, 1>::v]) {
   tv = __ldcs(t + (long long)t_stride * i);
 #pragma unroll
-  for (int j = 0; j < S::NQ; ++j) qv[j] = __ldcs(q + (long long)j * N + i);
+  for (int j = 0; j < S::NQ; ++j) qv[j] = __ldcs(q + (long long)j * ld + i);
 #pragma unroll
-  for (int j = 0; j < S::NX; ++j) xv[j] = __ldcs(x + (long long)j * N + i);
+  for (int j = 0; j < S::NX; ++j) xv[j] = __ldcs(x + (long long)j * ld + i);
 #pragma unroll
-  for (int j = 0; j < S::NY; ++j) yv[j] = __ldcs(y + (long long)j * N + i);
+  for (int j = 0; j < S::NY; ++j) yv[j] = __ldcs(y + (long long)j * ld + i);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
@@ -800,7 +805,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 // PF > 0: every thread also asks L2 for the inputs of the instance PF CTAs ahead (about one wave
 // of resident CTAs), so that the CTA scheduled there later finds its inputs in L2, not in DRAM.
 template <class S, int UNROLL, int PF = 0>
-__device__ __forceinline__ void pinv_step(long long N, const double* __restrict__ t, int t_stride,
+__device__ __forceinline__ void pinv_step(long long N, long long ld, const double* __restrict__ t, int t_stride,
                                           const double* __restrict__ q, const double* __restrict__ x,
                                           const double* __restrict__ y, double* __restrict__ qdot,
                                           double* __restrict__ xdot, int* __restrict__ mode) {
@@ -810,14 +815,14 @@ __device__ __forceinline__ void pinv_step(long long N, const double* __restrict_
       const long long ip = base + (long long)PF * blockDim.x * UNROLL;
       if (ip < N) {
 #pragma unroll
-        for (int k = 0; k < S::NIN; ++k) prefetch_l2(S::in_row(k, N, t, q, x, y) + ((k == 0 && S::T_STAGED && t_stride == 0) ? 0 : ip));
+        for (int k = 0; k < S::NIN; ++k) prefetch_l2(S::in_row(k, ld, t, q, x, y) + ((k == 0 && S::T_STAGED && t_stride == 0) ? 0 : ip));
       }
     }
     double tv[UNROLL], qv[UNROLL][Max<S::NQ, 1>::v], xv[UNROLL][Max<S::NX, 1>::v], yv[UNROLL][Max<S::NY, 1>::v];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long i = base + (long long)u * blockDim.x;
-      if (i < N) load_instance<S>(N, i, t, t_stride, q, x, y, tv[u], qv[u], xv[u], yv[u]);
+      if (i < N) load_instance<S>(ld, i, t, t_stride, q, x, y, tv[u], qv[u], xv[u], yv[u]);
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -825,7 +830,7 @@ __device__ __forceinline__ void pinv_step(long long N, const double* __restrict_
       if (i < N) {
         double v[S::NS];
         const int accepted = solve_instance<S>(tv[u], qv[u], xv[u], yv[u], v);
-        store_instance<S>(N, i, v, accepted, qdot, xdot, mode);
+        store_instance<S>(ld, i, v, accepted, qdot, xdot, mode);
       }
     }
   }
@@ -837,7 +842,7 @@ __device__ __forceinline__ void pinv_step(long long N, const double* __restrict_
 // t_k = t0 + k*dt, here for `steps` steps per instance without leaving the GPU.  The state update
 // is rounded like the notebook's NumPy code (separate multiply and add, no fma contraction).
 template <class S>
-__device__ __forceinline__ void pinv_rollout(long long N, int steps, double dt, const double* __restrict__ t0,
+__device__ __forceinline__ void pinv_rollout(long long N, long long ld, int steps, double dt, const double* __restrict__ t0,
                                              int t_stride, double* __restrict__ q, double* __restrict__ x,
                                              const double* __restrict__ y, double vmax_q, double vmax_x,
                                              double* __restrict__ qdot_last, double* __restrict__ xdot_last,
@@ -845,7 +850,7 @@ __device__ __forceinline__ void pinv_rollout(long long N, int steps, double dt, 
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
     double t0v, qv[Max<S::NQ, 1>::v], xv[Max<S::NX, 1>::v], yv[Max<S::NY, 1>::v];
-    load_instance<S>(N, i, t0, t_stride, q, x, y, t0v, qv, xv, yv);
+    load_instance<S>(ld, i, t0, t_stride, q, x, y, t0v, qv, xv, yv);
     double v[S::NS];
 #pragma unroll
     for (int j = 0; j < S::NS; ++j) v[j] = 0.0;
@@ -867,13 +872,13 @@ __device__ __forceinline__ void pinv_rollout(long long N, int steps, double dt, 
     }
 #pragma unroll
     for (int j = 0; j < S::NQ; ++j) {
-      q[(long long)j * N + i] = qv[j];
-      if (qdot_last != nullptr) qdot_last[(long long)j * N + i] = v[j];
+      q[(long long)j * ld + i] = qv[j];
+      if (qdot_last != nullptr) qdot_last[(long long)j * ld + i] = v[j];
     }
 #pragma unroll
     for (int j = 0; j < S::NX; ++j) {
-      x[(long long)j * N + i] = xv[j];
-      if (xdot_last != nullptr) xdot_last[(long long)j * N + i] = v[S::NQ + j];
+      x[(long long)j * ld + i] = xv[j];
+      if (xdot_last != nullptr) xdot_last[(long long)j * ld + i] = v[S::NQ + j];
     }
     if (mode_last != nullptr) mode_last[i] = accepted;
     if (n_failed != nullptr) n_failed[i] = failed;
@@ -920,7 +925,7 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
 }
 
 template <class S, int TILE, int STAGES>
-__device__ __forceinline__ void pinv_step_tma(long long N, const double* __restrict__ t, int t_stride,
+__device__ __forceinline__ void pinv_step_tma(long long N, long long ld, const double* __restrict__ t, int t_stride,
                                               const double* __restrict__ q, const double* __restrict__ x,
                                               const double* __restrict__ y, double* __restrict__ qdot,
                                               double* __restrict__ xdot, int* __restrict__ mode) {
@@ -936,7 +941,7 @@ __device__ __forceinline__ void pinv_step_tma(long long N, const double* __restr
     const unsigned bytes = cnt * 8u;
     mbar_expect_tx(&full[s], bytes * (unsigned)NIN);
 #pragma unroll
-    for (int k = 0; k < NIN; ++k) bulk_load(&buf[s][k][0], S::in_row(k, N, t, q, x, y) + i0, bytes, &full[s]);
+    for (int k = 0; k < NIN; ++k) bulk_load(&buf[s][k][0], S::in_row(k, ld, t, q, x, y) + i0, bytes, &full[s]);
   };
 
   if (tid == 0) {
@@ -971,7 +976,7 @@ __device__ __forceinline__ void pinv_step_tma(long long N, const double* __restr
     if (i < N) {
       double v[S::NS];
       const int accepted = solve_instance<S>(tv, qv, xv, yv, v);
-      store_instance<S>(N, i, v, accepted, qdot, xdot, mode);
+      store_instance<S>(ld, i, v, accepted, qdot, xdot, mode);
     }
     if (++s == STAGES) {
       s = 0;

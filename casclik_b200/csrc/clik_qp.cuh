@@ -794,7 +794,7 @@ template <class S> struct QpData {
 // is written.  MODE QP_TAIL: the full solver for such an instance, started from the parked prediction.
 enum : int { QP_FULL = 0, QP_FAST = 1, QP_TAIL = 2 };
 template <class S, int MODE>
-__device__ __forceinline__ void qp_instance(long long N, long long i, const double* __restrict__ t, int t_stride,
+__device__ __forceinline__ void qp_instance(long long ld, long long i, const double* __restrict__ t, int t_stride,
                                             const double* __restrict__ q, const double* __restrict__ x,
                                             const double* __restrict__ y, const double* __restrict__ x0,
                                             const unsigned* active0, double* __restrict__ sol,
@@ -802,11 +802,11 @@ __device__ __forceinline__ void qp_instance(long long N, long long i, const doub
   double qv[S::NQ > 0 ? S::NQ : 1], xv[S::NX > 0 ? S::NX : 1], yv[S::NY > 0 ? S::NY : 1];
   const double tv = __ldcs(t + (long long)t_stride * i);
 #pragma unroll
-  for (int j = 0; j < S::NQ; ++j) qv[j] = __ldcs(q + (long long)j * N + i);
+  for (int j = 0; j < S::NQ; ++j) qv[j] = __ldcs(q + (long long)j * ld + i);
 #pragma unroll
-  for (int j = 0; j < S::NX; ++j) xv[j] = __ldcs(x + (long long)j * N + i);
+  for (int j = 0; j < S::NX; ++j) xv[j] = __ldcs(x + (long long)j * ld + i);
 #pragma unroll
-  for (int j = 0; j < S::NY; ++j) yv[j] = __ldcs(y + (long long)j * N + i);
+  for (int j = 0; j < S::NY; ++j) yv[j] = __ldcs(y + (long long)j * ld + i);
   double xs[S::QN];
   unsigned mu, ml;
   int st;
@@ -819,14 +819,14 @@ __device__ __forceinline__ void qp_instance(long long N, long long i, const doub
     const bool parked = MODE == QP_TAIL && active != nullptr;
     if (parked) {
       wu = active[i];
-      wl = active[N + i];
+      wl = active[ld + i];
     } else if (active0 != nullptr) {
       wu = active0[i];
-      wl = active0[N + i];
+      wl = active0[ld + i];
     } else if (x0 != nullptr) {
       double x0v[S::QN];
 #pragma unroll
-      for (int j = 0; j < S::QN; ++j) x0v[j] = x0[(long long)j * N + i];
+      for (int j = 0; j < S::QN; ++j) x0v[j] = x0[(long long)j * ld + i];
       masks_from_x0<S>(d, x0v, &wu, &wl);
     } else if (!S::QP_CRASH && S::QP_EQ_START) {
       // no guess: equality rows are active at every solution, start with them held
@@ -847,7 +847,7 @@ __device__ __forceinline__ void qp_instance(long long N, long long i, const doub
         status[i] = QP_PENDING;
         if (active != nullptr) {
           active[i] = wu;
-          active[N + i] = wl;
+          active[ld + i] = wl;
         }
         return;
       }
@@ -868,28 +868,28 @@ __device__ __forceinline__ void qp_instance(long long N, long long i, const doub
     st = qp_dual_active_set<S::QN, S::QM>(S::QN, S::QM, d.A, d.lb, d.ub, d.h, nullptr, xs, &mu, &ml,
                                           max_iter);
   }
-  for (int j = 0; j < S::QN; ++j) __stcs(sol + (long long)j * N + i, xs[j]);
+  for (int j = 0; j < S::QN; ++j) __stcs(sol + (long long)j * ld + i, xs[j]);
   if (status != nullptr) status[i] = st;
   if (active != nullptr) {
     active[i] = mu;
-    active[N + i] = ml;
+    active[ld + i] = ml;
   }
 }
 
-// Fused step, SoA in / SoA out: sol[j*N + i] is entry j of x for instance i; active[i] = upper mask,
-// active[N + i] = lower mask.  One kernel does everything (MODE = QP_FULL), or — structured skills with
+// Fused step, SoA in / SoA out: sol[j*ld + i] is entry j of x for instance i; active[i] = upper mask,
+// active[ld + i] = lower mask (N instances, row stride ld >= N: see pinv_step).  One kernel does everything (MODE = QP_FULL), or — structured skills with
 // the working-set prediction, status array present — a QP_FAST pass followed by qp_step_tail.  The split
 // keeps the Goldfarb-Idnani iteration (255 registers + spills, needed by well under 1 % of the
 // instances) out of the kernel every instance runs (159 registers for the UR5 problem).
 template <class S, int MODE>
-__device__ __forceinline__ void qp_step(long long N, const double* __restrict__ t, int t_stride,
+__device__ __forceinline__ void qp_step(long long N, long long ld, const double* __restrict__ t, int t_stride,
                                         const double* __restrict__ q, const double* __restrict__ x,
                                         const double* __restrict__ y, const double* __restrict__ x0,
                                         const unsigned* active0, double* __restrict__ sol,
                                         int* __restrict__ status, unsigned* active, int max_iter) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
-    qp_instance<S, MODE>(N, i, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);
+    qp_instance<S, MODE>(ld, i, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);
 }
 
 // Tail pass: every CTA scans QP_TAIL_TILE consecutive status entries, collects the instances the FAST
@@ -898,7 +898,7 @@ __device__ __forceinline__ void qp_step(long long N, const double* __restrict__ 
 constexpr int QP_TAIL_TILE = 1024;
 #ifdef __CUDACC__   // (the host-compiled test harness of the solvers has no shared memory)
 template <class S>
-__device__ __forceinline__ void qp_step_tail(long long N, const double* __restrict__ t, int t_stride,
+__device__ __forceinline__ void qp_step_tail(long long N, long long ld, const double* __restrict__ t, int t_stride,
                                              const double* __restrict__ q, const double* __restrict__ x,
                                              const double* __restrict__ y, const double* __restrict__ x0,
                                              const unsigned* active0, double* __restrict__ sol,
@@ -914,7 +914,7 @@ __device__ __forceinline__ void qp_step_tail(long long N, const double* __restri
     __syncthreads();
     const int n = count;
     for (int k = threadIdx.x; k < n; k += blockDim.x)
-      qp_instance<S, QP_TAIL>(N, base + list[k], t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);
+      qp_instance<S, QP_TAIL>(ld, base + list[k], t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);
     __syncthreads();
   }
 }
@@ -926,7 +926,7 @@ __device__ __forceinline__ void qp_step_tail(long long N, const double* __restri
 // ur5_moe2016_example2.ipynb cell 12).  A step whose QP is not solved (status != 0; the reference
 // would raise there) applies zero velocity and is counted in n_failed.
 template <class S>
-__device__ __forceinline__ void qp_rollout(long long N, int steps, double dt, const double* __restrict__ t0,
+__device__ __forceinline__ void qp_rollout(long long N, long long ld, int steps, double dt, const double* __restrict__ t0,
                                            int t_stride, double* __restrict__ q, double* __restrict__ x,
                                            const double* __restrict__ y, double vmax_q, double vmax_x,
                                            double* __restrict__ sol_last, int* __restrict__ n_failed,
@@ -935,9 +935,9 @@ __device__ __forceinline__ void qp_rollout(long long N, int steps, double dt, co
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
     double qv[S::NQ > 0 ? S::NQ : 1], xv[S::NX > 0 ? S::NX : 1], yv[S::NY > 0 ? S::NY : 1];
     const double t0v = t0[(long long)t_stride * i];
-    for (int j = 0; j < S::NQ; ++j) qv[j] = q[(long long)j * N + i];
-    for (int j = 0; j < S::NX; ++j) xv[j] = x[(long long)j * N + i];
-    for (int j = 0; j < S::NY; ++j) yv[j] = y[(long long)j * N + i];
+    for (int j = 0; j < S::NQ; ++j) qv[j] = q[(long long)j * ld + i];
+    for (int j = 0; j < S::NX; ++j) xv[j] = x[(long long)j * ld + i];
+    for (int j = 0; j < S::NY; ++j) yv[j] = y[(long long)j * ld + i];
     double xs[S::QN];
     for (int j = 0; j < S::QN; ++j) xs[j] = 0.0;
     int failed = 0;
@@ -981,10 +981,10 @@ __device__ __forceinline__ void qp_rollout(long long N, int steps, double dt, co
         xv[j] = __dadd_rn(xv[j], __dmul_rn(xs[S::NQ + j], dt));
       }
     }
-    for (int j = 0; j < S::NQ; ++j) q[(long long)j * N + i] = qv[j];
-    for (int j = 0; j < S::NX; ++j) x[(long long)j * N + i] = xv[j];
+    for (int j = 0; j < S::NQ; ++j) q[(long long)j * ld + i] = qv[j];
+    for (int j = 0; j < S::NX; ++j) x[(long long)j * ld + i] = xv[j];
     if (sol_last != nullptr)
-      for (int j = 0; j < S::QN; ++j) sol_last[(long long)j * N + i] = xs[j];
+      for (int j = 0; j < S::QN; ++j) sol_last[(long long)j * ld + i] = xs[j];
     if (n_failed != nullptr) n_failed[i] = failed;
   }
 }

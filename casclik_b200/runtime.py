@@ -14,7 +14,7 @@ _c_double_p = ctypes.POINTER(ctypes.c_double)
 _c_int32_p = ctypes.POINTER(ctypes.c_int32)
 _c_uint32_p = ctypes.POINTER(ctypes.c_uint32)
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 QP_SOLVED, QP_MAXITER, QP_INFEASIBLE = 0, 1, 2
 
 
@@ -33,6 +33,7 @@ EXPORTS = (
     "clik_skill_load", "clik_skill_free", "clik_pinv_step", "clik_pinv_rollout", "clik_qp_step",
     "clik_qp_rollout", "clik_qp_dense",
     "clik_pinv_step_host", "clik_qp_step_host", "clik_skill_launch_info",
+    "clik_pinv_step_ld", "clik_qp_step_ld", "clik_pinv_step_host_multi", "clik_qp_step_host_multi",
     "clik_measure_fp64_peak", "clik_flush_l2", "clik_device_count", "clik_abi_version",
     "clik_last_error",
 )
@@ -71,6 +72,15 @@ def load_library():
     lib.clik_pinv_step.argtypes = [vp, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.clik_pinv_step_host.restype = i32
     lib.clik_pinv_step_host.argtypes = [vp, i64, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.clik_pinv_step_ld.restype = i32
+    lib.clik_pinv_step_ld.argtypes = [vp, i64, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.clik_qp_step_ld.restype = i32
+    lib.clik_qp_step_ld.argtypes = [vp, i64, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
+    lib.clik_pinv_step_host_multi.restype = i32
+    lib.clik_pinv_step_host_multi.argtypes = [ctypes.POINTER(vp), i32, i64, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.clik_qp_step_host_multi.restype = i32
+    lib.clik_qp_step_host_multi.argtypes = [ctypes.POINTER(vp), i32, i64, vp, i32, vp, vp, vp, vp, vp, vp,
+                                            vp, vp, i32]
     lib.clik_pinv_rollout.restype = i32
     lib.clik_pinv_rollout.argtypes = [vp, i64, i32, ctypes.c_double, vp, i32, vp, vp, vp,
                                       ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, vp]
@@ -111,9 +121,12 @@ def require_device():
 
 
 def current_device():
-    """Device ordinal to load skills on: LOCAL_RANK under torchrun, else torch's current device
-    if torch has been imported, else 0."""
+    """Device ordinal used when the caller gives no device (host-array batches): LOCAL_RANK under
+    torchrun, else torch's current device if torch has been imported, else 0.  Batches of CUDA
+    tensors never come here: they run on the device the tensors live on."""
     import sys
+    if "LOCAL_RANK" in os.environ:
+        return int(os.environ["LOCAL_RANK"])
     if "torch" in sys.modules:
         torch = sys.modules["torch"]
         try:
@@ -154,6 +167,22 @@ def host_ptr(arr, dtype, numel, what):
     if a.size != numel:
         raise ClikError("%s has %d elements, expected %d" % (what, a.size, numel))
     return ctypes.c_void_p(a.ctypes.data), a
+
+
+def host_out_ptr(arr, dtype, numel, what):
+    """Pointer of a caller-supplied OUTPUT array: it is written in place, so it is never copied or
+    converted — a buffer of the wrong dtype, size or layout is an error, not something to fix up."""
+    if arr is None:
+        return None
+    if not isinstance(arr, np.ndarray):
+        raise ClikError("%s must be a NumPy array when the inputs are host arrays" % what)
+    if arr.dtype != np.dtype(dtype) and not (np.dtype(dtype) == np.int32 and arr.dtype == np.uint32):
+        raise ClikError("%s must have dtype %s, got %s" % (what, np.dtype(dtype), arr.dtype))
+    if not arr.flags["C_CONTIGUOUS"] or not arr.flags["WRITEABLE"]:
+        raise ClikError("%s must be a writeable C-contiguous array (structure-of-arrays: shape (rows, N))" % what)
+    if arr.size != numel:
+        raise ClikError("%s has %d elements, expected %d" % (what, arr.size, numel))
+    return ctypes.c_void_p(arr.ctypes.data)
 
 
 class CompiledSkill(object):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CLIK_ABI_VERSION 1
+#define CLIK_ABI_VERSION 2
 
 typedef enum {
   CLIK_OK = 0,
@@ -83,6 +83,15 @@ clik_status clik_pinv_step(const clik_skill* skill, int64_t N, const double* t, 
                            const double* q, const double* x, const double* y, double* qdot,
                            double* xdot, int32_t* mode, void* stream);
 
+/* The same step for one SHARD of a larger batch, without repacking: N instances are processed, rows of
+ * every array are `ld` elements apart (ld >= N), and every pointer (t when t_stride = 1, q, x, y, qdot,
+ * xdot, mode) already points at the shard's first instance.  clik_pinv_step(..N..) == clik_pinv_step_ld(..N, N..).
+ * This is how one batch is split over the GPUs of a box (BASELINE.json north_star: "sharded across the
+ * 8 GPUs ... no NCCL on the hot path"): shard k of a mapped host batch runs on device k in place. */
+clik_status clik_pinv_step_ld(const clik_skill* skill, int64_t N, int64_t ld, const double* t,
+                              int32_t t_stride, const double* q, const double* x, const double* y,
+                              double* qdot, double* xdot, int32_t* mode, void* stream);
+
 /* The simulation loop CASCLIK users run around solve() (examples/notebooks/ur5_moe2016_example2.ipynb
  * cell 12, raw lines :535-549), `steps` controller steps per instance on the device:
  *     v = solve(t0 + k*dt, q, x, y);  v = clip(v, +-max_speed);  q += v_rob*dt;  x += v_virt*dt
@@ -114,6 +123,12 @@ clik_status clik_qp_step(const clik_skill* skill, int64_t N, const double* t, in
                          const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
                          int32_t max_iter, void* stream);
 
+/* Shard variant of clik_qp_step (see clik_pinv_step_ld): active[i] / active[ld + i]. */
+clik_status clik_qp_step_ld(const clik_skill* skill, int64_t N, int64_t ld, const double* t,
+                            int32_t t_stride, const double* q, const double* x, const double* y,
+                            const double* x0, const uint32_t* active0, double* sol, int32_t* status,
+                            uint32_t* active, int32_t max_iter, void* stream);
+
 /* The same simulation loop with the QP controller (see clik_pinv_rollout).  A step whose QP is not
  * solved applies zero velocity and is counted in n_failed (the reference would raise there).
  *   sol_last [qp_n * N] out, may be NULL: solution of the last step (robot part clipped) */
@@ -142,6 +157,22 @@ clik_status clik_qp_step_host(const clik_skill* skill, int64_t N, const double* 
                               const double* q, const double* x, const double* y, const double* x0,
                               const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
                               int32_t max_iter);
+
+/* One host batch over several GPUs of the box: `skills[k]` is the same cubin loaded on device k
+ * (clik_skill_load with desc.device = k); the batch is cut into n_skills contiguous shards (sizes differ
+ * by at most one, shard k = [k*N/n .. )), each shard runs on its device from its own host thread (zero
+ * copy on page-locked buffers — the SMs of device k read/write only shard k of the host arrays over that
+ * device's PCIe link — or the chunked pipeline on pageable ones), and the call returns when every
+ * result is in the caller's host arrays: the "final host gather" of the north star, with no collective
+ * and no intermediate copy.  Results are bit-identical to the single-device call. */
+clik_status clik_pinv_step_host_multi(const clik_skill* const* skills, int32_t n_skills, int64_t N,
+                                      const double* t, int32_t t_stride, const double* q,
+                                      const double* x, const double* y, double* qdot, double* xdot,
+                                      int32_t* mode);
+clik_status clik_qp_step_host_multi(const clik_skill* const* skills, int32_t n_skills, int64_t N,
+                                    const double* t, int32_t t_stride, const double* q, const double* x,
+                                    const double* y, const double* x0, const uint32_t* active0,
+                                    double* sol, int32_t* status, uint32_t* active, int32_t max_iter);
 
 /* Launch geometry chosen at load time (for reporting). */
 clik_status clik_skill_launch_info(const clik_skill* skill, int32_t which /*0 pinv, 1 qp, 2 pinv TMA-staged, 3 qp fast pass, 4 qp tail pass*/,

@@ -42,6 +42,10 @@ static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline int __double2int_rn(double x) { return (int)std::nearbyint(x); }
+static inline int __double2hiint(double x) { long long b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
+static inline int __double2loint(double x) { long long b; std::memcpy(&b, &x, 8); return (int)(b & 0xffffffffLL); }
+static inline double __hiloint2double(int hi, int lo) {
+  unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo; double x; std::memcpy(&x, &b, 8); return x; }
 static inline unsigned __activemask() { return 1u; }
 static inline int __any_sync(unsigned, int p) { return p; }
 static inline void __syncthreads() {}
@@ -89,7 +93,7 @@ def test_pinv_kernel_source_on_host_reproduces_the_reference_outputs(name, tmp_p
     nx = 0 if x is None else x.shape[0]
     qdot, xdot = np.full((nq, N), np.nan), (np.full((nx, N), np.nan) if nx else None)
     mode = np.full(N, -9, dtype=np.int32)
-    lib.clik_pinv_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), _p(qdot), _p(xdot), _p(mode))
+    lib.clik_pinv_kernel(ctypes.c_longlong(N), ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), _p(qdot), _p(xdot), _p(mode))
     got = qdot if xdot is None else np.vstack([qdot, xdot])
     gv, gmode = golden_velocities(outputs)
     assert np.array_equal(mode, gmode)
@@ -108,7 +112,7 @@ def test_pinv_kernel_source_on_host_reproduces_the_reference_outputs(name, tmp_p
         ts = np.ascontiguousarray(t[:n])
         inf = float("inf")
         lib.clik_pinv_rollout_kernel(
-            ctypes.c_longlong(n), ctypes.c_int(cfg["steps"]), ctypes.c_double(cfg["dt"]), _p(ts), ctypes.c_int(1),
+            ctypes.c_longlong(n), ctypes.c_longlong(n), ctypes.c_int(cfg["steps"]), ctypes.c_double(cfg["dt"]), _p(ts), ctypes.c_int(1),
             _p(qs), _p(xs), _p(ys), ctypes.c_double(inf if cfg["max_speed"] is None else cfg["max_speed"]),
             ctypes.c_double(inf if cfg["max_virtual_speed"] is None else cfg["max_virtual_speed"]),
             None, None, None, None)
@@ -128,7 +132,7 @@ def test_qp_kernel_source_on_host_reproduces_the_reference_minimisers(name, tmp_
     sol = np.full((nqp, N), np.nan)
     status = np.full(N, -9, dtype=np.int32)
     active = np.zeros((2, N), dtype=np.uint32)
-    lib.clik_qp_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), None, None, _p(sol),
+    lib.clik_qp_kernel(ctypes.c_longlong(N), ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), None, None, _p(sol),
                        _p(status), _p(active), ctypes.c_int(10 * (nqp + gA.shape[1])))
     assert np.all(status == 0)
     for i in range(N):
@@ -145,7 +149,7 @@ def test_qp_kernel_source_on_host_reproduces_the_reference_minimisers(name, tmp_
         failed = np.full(n, -9, dtype=np.int32)
         inf = float("inf")
         lib.clik_qp_rollout_kernel(
-            ctypes.c_longlong(n), ctypes.c_int(cfg["steps"]), ctypes.c_double(cfg["dt"]), _p(ts), ctypes.c_int(1),
+            ctypes.c_longlong(n), ctypes.c_longlong(n), ctypes.c_int(cfg["steps"]), ctypes.c_double(cfg["dt"]), _p(ts), ctypes.c_int(1),
             _p(qs), _p(xs), _p(ys), ctypes.c_double(inf if cfg["max_speed"] is None else cfg["max_speed"]),
             ctypes.c_double(inf if cfg["max_virtual_speed"] is None else cfg["max_virtual_speed"]),
             None, _p(failed), ctypes.c_int(10 * (nqp + gA.shape[1])))
@@ -153,7 +157,7 @@ def test_qp_kernel_source_on_host_reproduces_the_reference_minimisers(name, tmp_
         assert np.all(failed == 0) and np.abs(qs - want).max() <= 1e-7 * (1 + np.abs(want).max())
     if ctrl.kernel_meta.get("qp_split"):                     # prediction pass + tail pass, as the ABI launches them
         sol2, status2, active2 = np.full_like(sol, np.nan), np.full_like(status, -9), np.zeros_like(active)
-        args = (ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), None, None, _p(sol2), _p(status2),
+        args = (ctypes.c_longlong(N), ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), None, None, _p(sol2), _p(status2),
                 _p(active2), ctypes.c_int(10 * (nqp + gA.shape[1])))
         lib.clik_qp_fast_kernel(*args)
         assert set(np.unique(status2)) <= {0, 3}
@@ -175,7 +179,7 @@ def test_benchmark_scenarios_kernel_source_on_host_vs_oracle(name, tmp_path):
     t, q, x, y = _inputs(inp)
     nq = q.shape[0]
     qdot, mode = np.full((nq, N), np.nan), np.full(N, -9, dtype=np.int32)
-    lib.clik_pinv_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), _p(qdot), None, _p(mode))
+    lib.clik_pinv_kernel(ctypes.c_longlong(N), ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), _p(qdot), None, _p(mode))
     ref_v, ref_mode = oracle_pinv(sc.spec, inp, dict(sc.options) if sc.options else None)
     assert np.array_equal(mode, ref_mode)
     assert len(np.unique(ref_mode)) >= (1 if name == "ur5_track" else 2)
@@ -196,7 +200,7 @@ def test_benchmark_qp_scenarios_kernel_source_on_host_vs_oracle(name, tmp_path):
     nqp, m = A.shape[2], A.shape[1]
     sol, status = np.full((nqp, N), np.nan), np.full(N, -9, dtype=np.int32)
     active = np.zeros((2, N), dtype=np.uint32)
-    lib.clik_qp_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), None, None, _p(sol),
+    lib.clik_qp_kernel(ctypes.c_longlong(N), ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), None, None, _p(sol),
                        _p(status), _p(active), ctypes.c_int(10 * (nqp + m)))
     assert np.all(status == 0)
     for i in range(N):
@@ -233,7 +237,7 @@ def test_mode_search_variants_agree_with_the_oracle(env, tmp_path, monkeypatch):
         inp["q"][j, i] = np.where(rng.random(len(j)) < 0.5, -3.2, 3.2)
     t, q, x, y = _inputs(inp)
     qdot, mode = np.full((7, N), np.nan), np.full(N, -9, dtype=np.int32)
-    lib.clik_pinv_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), _p(qdot), None, _p(mode))
+    lib.clik_pinv_kernel(ctypes.c_longlong(N), ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), _p(qdot), None, _p(mode))
     ref_v, ref_mode = oracle_pinv(sc.spec, inp)
     assert np.array_equal(mode, ref_mode)
     assert len(np.unique(ref_mode)) > 40 and ref_mode.max() > 60
@@ -258,7 +262,7 @@ def test_dense_sets_take_the_dynamic_tail(tmp_path):
     inp = {"t": rng.uniform(0, 5, N), "q": rng.uniform(-0.9, 0.9, (5, N))}
     t_, q_, _, _ = _inputs(inp)
     qdot, mode = np.full((5, N), np.nan), np.full(N, -9, dtype=np.int32)
-    lib.clik_pinv_kernel(ctypes.c_longlong(N), _p(t_), ctypes.c_int(1), _p(q_), None, None, _p(qdot), None, _p(mode))
+    lib.clik_pinv_kernel(ctypes.c_longlong(N), ctypes.c_longlong(N), _p(t_), ctypes.c_int(1), _p(q_), None, None, _p(qdot), None, _p(mode))
     ref_v, ref_mode = oracle_pinv(spec, inp)
     assert np.array_equal(mode, ref_mode)
     assert (ref_mode >= 11).sum() > 20 and (ref_mode == -1).sum() >= 0
@@ -285,7 +289,7 @@ def test_fuzzed_skills_kernel_source_on_host_vs_oracle(seed, tmp_path):
         inp = dict(inp, x=x)
     qdot, xdot = np.full((nq, N), np.nan), (np.full((nx, N), np.nan) if nx else None)
     mode = np.full(N, -9, dtype=np.int32)
-    lib.clik_pinv_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y if ctrl._ny else None),
+    lib.clik_pinv_kernel(ctypes.c_longlong(N), ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y if ctrl._ny else None),
                          _p(qdot), _p(xdot), _p(mode))
     got = qdot if xdot is None else np.vstack([qdot, xdot])
     ref_v, ref_mode = oracle_pinv(spec, inp, dict(opts))
@@ -316,7 +320,7 @@ def test_fuzzed_qp_skills_kernel_source_on_host_vs_oracle(seed, tmp_path):
     m, nqp = A.shape[1], A.shape[2]
     sol, status = np.full((nqp, N), np.nan), np.full(N, -9, dtype=np.int32)
     active = np.zeros((2, N), dtype=np.uint32)
-    lib.clik_qp_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y if ctrl._ny else None), None, None,
+    lib.clik_qp_kernel(ctypes.c_longlong(N), ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y if ctrl._ny else None), None, None,
                        _p(sol), _p(status), _p(active), ctypes.c_int(10 * (nqp + m)))
     for i in range(N):
         xo, lamo, sto = orc.solve_qp_single(h, A[i], lb[i], ub[i])
@@ -341,7 +345,7 @@ def test_fuzzed_option_skills_kernel_source_on_host_vs_oracle(seed, tmp_path):
     t, q, x, y = _inputs(inp)
     nq, N = q.shape
     qdot, mode = np.full((nq, N), np.nan), np.full(N, -9, dtype=np.int32)
-    lib.clik_pinv_kernel(ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), None, None, _p(qdot), None, _p(mode))
+    lib.clik_pinv_kernel(ctypes.c_longlong(N), ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), None, None, _p(qdot), None, _p(mode))
     ref_v, ref_mode = oracle_pinv(spec, inp, dict(opts))
     assert np.array_equal(mode, ref_mode) and len(np.unique(ref_mode)) >= 2
     err = np.linalg.norm(qdot - ref_v, axis=0) / np.maximum(np.linalg.norm(ref_v, axis=0), 1e-12)
