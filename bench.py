@@ -2,7 +2,7 @@
 """bench.py — controller-steps/sec of the batched CLIK controller step on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--scenario ur5_track] [--batch 1048576]
+                    [--scenario ur5_track] [--batch 1048576] [--no-secondary]
 
 A "step" is one pass of the hot path (PseudoInverseController.solve for every instance of the
 batch — reference casclik/controllers/pseudo_inverse.py:512-556) over one batch of synthetic
@@ -10,10 +10,15 @@ inputs (BASELINE.json configs[1]: UR5, one EqualityConstraint, 2^20 random joint
 per GPU, fp64).  One JSON line is printed by rank 0; see the keys at the bottom.
 
 Timing: W warm-up steps, then exactly K steps between (barrier + synchronize), timed with CUDA
-events on the launch stream, MAX over ranks.  The step rotates over several resident input sets
-whose total size exceeds L2 (126 MB), so no step re-reads a cache-resident batch.
-`value` times device-resident inputs; `e2e` times the same step through the host-buffer C ABI
-(pinned host inputs, H2D + kernel + D2H inside the timed region).
+events on the launch stream, MAX over ranks.  The step rotates over several resident input AND
+output sets whose total size exceeds L2 (126 MB), so no step re-reads a cache-resident batch and
+every result has to reach DRAM.  `value` times device-resident inputs; `e2e` times the same step
+through the host-buffer C ABI (pinned host inputs, H2D + kernel + D2H inside the timed region).
+
+`secondary` (same JSON line) carries the other BASELINE configs measured the same way in the same
+run — configs[2] iiwa multi-task 2^20, configs[3] UR5 QP 2^18, configs[4] Moe-2016 SRMTP and QP with
+a global batch of 2^23 sharded over the ranks — each with its own roofline and CPU baseline.
+
 `--impl reference` times the restated reference CPU path (oracle/clik_oracle.c, all host
 threads) on a bounded sample of the same workload.
 """
@@ -33,6 +38,14 @@ sys.path.insert(0, ROOT)
 METRIC = "controller-steps/sec (fp64, batch N)"
 UNIT = "controller-steps/s"
 
+#: BASELINE.json configs measured next to the headline one: (scenario, batch, "weak" = per GPU | "strong" = global)
+SECONDARY = (
+    ("iiwa_multitask", 1 << 20, "weak", "configs[2]"),
+    ("ur5_qp", 1 << 18, "weak", "configs[3]"),
+    ("ur5_moe2016_pinv", 1 << 23, "strong", "configs[4] SRMTP"),
+    ("ur5_moe2016_qp", 1 << 23, "strong", "configs[4] ReactiveQP"),
+)
+
 
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -41,6 +54,16 @@ def _peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _ncu_counts():
+    """Per-scenario figures taken from ncu captures of this bench (profiles/r2_ncu_counts.json, written by
+    tools/ncu_counts.py): DRAM bytes per launch and EXECUTED fp64 thread-instructions per instance."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_counts.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
 
 
 class ClockSampler(threading.Thread):
@@ -99,32 +122,55 @@ def _launch_info(ctrl, is_qp):
     return info
 
 
-def cpu_reference(scenario, batch, seconds_target=12.0, threads=0):
-    """Restated reference CPU path (oracle/clik_oracle.c) on a bounded sample of the workload."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import c_port
-    import clik_oracle as orc
-    from casclik_b200 import fk
-    if scenario.name != "ur5_track":
-        raise SystemExit("CPU baseline is implemented for the ur5_track workload")
-    chain = orc.load_chain(fk.UR5_URDF, "base_link", "tool0")
-    cores = c_port.max_threads() if threads <= 0 else threads
-    n = 4096
-    inp = scenario.sample(n, seed=0)
-    c_port.pinv_track(chain, inp["q"], inp["y"], threads=cores)          # warm
-    t0 = time.perf_counter()
-    c_port.pinv_track(chain, inp["q"], inp["y"], threads=cores)
-    rate = n / max(time.perf_counter() - t0, 1e-9)
-    sample = int(min(batch, max(4096, rate * seconds_target)))
-    passes = max(1, int(round(rate * seconds_target / sample)))
-    inp = scenario.sample(sample, seed=0)
-    t0 = time.perf_counter()
-    for _ in range(passes):
-        _, used = c_port.pinv_track(chain, inp["q"], inp["y"], threads=cores)
-    dt = time.perf_counter() - t0
-    return {"value": sample * passes / dt, "unit": UNIT, "cores": int(used), "kind": "port",
-            "sample": "%d passes over the first %d instances of the %d-instance batch, %.2f s wall, "
-                      "oracle/clik_oracle.c (gcc -O2 -fopenmp)" % (passes, sample, batch, dt)}, sample, dt
+# ---- reference CPU path --------------------------------------------------------------------------------
+
+class CpuPort(object):
+    """The restated reference CPU path of one scenario (oracle/, the one place bench.py may execute it):
+    ur5_track -> the hand-written FK + literal pinv of round 1 (cheaper than AD code: errs in the
+    reference's favour); every other scenario -> generated expression C + literal per-mode algebra +
+    mode search / dual active-set QP (oracle/clik_oracle.c, generic part)."""
+
+    def __init__(self, scenario):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import c_port
+        self.c_port, self.scenario = c_port, scenario
+        if scenario.name == "ur5_track":
+            import clik_oracle as orc
+            from casclik_b200 import fk
+            self.chain = orc.load_chain(fk.UR5_URDF, "base_link", "tool0")
+            self.port = None
+            self.what = "oracle/clik_oracle.c:clik_ref_pinv_track (gcc -O2 -fopenmp)"
+        elif scenario.controller == "qp":
+            self.port = c_port.QpPort(scenario.spec)
+            self.what = "oracle/clik_oracle.c:clik_ref_qp_batch + generated expression C (gcc -O2 -fopenmp)"
+        else:
+            self.port = c_port.PinvPort(scenario.spec, scenario.options)
+            self.what = "oracle/clik_oracle.c:clik_ref_pinv_batch + generated expression C (gcc -O2 -fopenmp)"
+        self.cores = c_port.max_threads()
+
+    def run(self, inp):
+        if self.port is None:
+            return self.c_port.pinv_track(self.chain, inp["q"], inp["y"], threads=self.cores)[1]
+        return self.port.solve(inp, threads=self.cores)[-1]
+
+    def measure(self, batch, seconds_target):
+        """-> (cpu_baseline dict, sample size, wall seconds)"""
+        n = 4096
+        inp = self.scenario.sample(n, seed=0)
+        self.run(inp)                                                     # warm
+        t0 = time.perf_counter()
+        self.run(inp)
+        rate = n / max(time.perf_counter() - t0, 1e-9)
+        sample = int(min(batch, max(4096, rate * seconds_target)))
+        passes = max(1, int(round(rate * seconds_target / sample)))
+        inp = self.scenario.sample(sample, seed=0)
+        t0 = time.perf_counter()
+        for _ in range(passes):
+            used = self.run(inp)
+        dt = time.perf_counter() - t0
+        return {"value": sample * passes / dt, "unit": UNIT, "cores": int(used), "kind": "port",
+                "sample": "%d passes over the first %d instances of the %d-instance batch, %.2f s wall, %s"
+                          % (passes, sample, batch, dt, self.what)}, sample, dt
 
 
 def run_reference(args, scenario, rank, world):
@@ -134,35 +180,165 @@ def run_reference(args, scenario, rank, world):
     # bounded: every step is a sample of the batch sized so that the whole run (warm-up + K
     # steps) costs about two minutes of host time
     budget = 120.0 / (steps + min(warm, 3))
-    base, sample, dt = cpu_reference(scenario, args.batch, seconds_target=budget)
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import c_port
-    import clik_oracle as orc
-    from casclik_b200 import fk
-    chain = orc.load_chain(fk.UR5_URDF, "base_link", "tool0")
+    port = CpuPort(scenario)
+    base, sample, dt = port.measure(args.batch, seconds_target=budget)
     inp = scenario.sample(sample, seed=0)
     for _ in range(min(warm, 3)):
-        c_port.pinv_track(chain, inp["q"], inp["y"], threads=base["cores"])
+        port.run(inp)
     t0 = time.perf_counter()
     for _ in range(steps):
-        c_port.pinv_track(chain, inp["q"], inp["y"], threads=base["cores"])
+        port.run(inp)
     dt = time.perf_counter() - t0
     value = sample * steps / dt
     base["value"] = value
-    base["sample"] = ("%d-instance sample of the %d-instance batch per step, %d steps, %.2f s wall, "
-                      "oracle/clik_oracle.c (gcc -O2 -fopenmp)" % (sample, args.batch, steps, dt))
-    print(json.dumps({
+    base["sample"] = ("%d-instance sample of the %d-instance batch per step, %d steps, %.2f s wall, %s"
+                      % (sample, args.batch, steps, dt, port.what))
+    line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": scenario.description, "scenario": scenario.name,
-                   "batch_per_step": sample,
+                   "batch_per_gpu": args.batch, "batch_per_step": sample,
                    "note": "reference CPU path restated in C (CasADi/qpOASES are not installable "
                            "here); host threads only, no GPU"},
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }
+    if not args.no_secondary:
+        from casclik_b200 import scenarios
+        sec = {}
+        for name, batch, _, cfg in SECONDARY:
+            try:
+                sc = scenarios.get(name)
+                b, _, _ = CpuPort(sc).measure(batch, seconds_target=6.0)
+                sec[name] = {"config": cfg, "value": b["value"], "unit": UNIT, "cpu_baseline": b}
+            except Exception as exc:      # the headline line must survive a broken secondary leg
+                sec[name] = {"config": cfg, "error": "%s: %s" % (type(exc).__name__, exc)}
+        line["secondary"] = sec
+    print(json.dumps(line))
+
+
+# ---- our arm ---------------------------------------------------------------------------------------------
+
+def _launches_per_step(meta, is_qp):
+    """Kernels of ours per step: QP skills with the working-set prediction run a fast + a tail launch,
+    pinv skills with a run-time mode tail a fast + a group launch (both when the status / mode array is given)."""
+    if is_qp:
+        return 2 if (meta.get("qp_split") and os.environ.get("CLIK_QP_SPLIT", "1") != "0") else 1
+    if os.environ.get("CLIK_PINV_GROUP", "0") == "1":
+        return 1
+    return 2 if (meta.get("pinv_split") and os.environ.get("CLIK_PINV_SPLIT", "1") != "0") else 1
+
+
+def _bytes_per_set(meta, is_qp, B):
+    return (meta["qp_bytes_per_step"] if is_qp else meta["pinv_bytes_per_step"]) * B
+
+
+def time_device_resident(torch, dist, ctrl, scenario, B, steps, warm, rank, world, dev, min_sets=2,
+                         seed_base=1000):
+    """K steps of solve_batch on device-resident inputs -> (ms total max-over-ranks, n_sets, graph?, step).
+    Inputs and outputs rotate over enough sets to exceed L2 twice over."""
+    meta = ctrl.kernel_meta
+    is_qp = scenario.controller == "qp"
+    per_set = _bytes_per_set(meta, is_qp, B)
+    n_sets = int(max(min_sets, min(16, -(-(300 << 20) // max(per_set, 1)))))
+    ins, outs = [], []
+    for s in range(n_sets):
+        inp = scenario.sample(B, seed=seed_base * (rank + 1) + s)
+        ins.append(tuple(None if inp[k] is None else torch.from_numpy(np.ascontiguousarray(inp[k])).to(dev)
+                         for k in ("t", "q", "x", "y")))
+        if is_qp:
+            outs.append((torch.empty((meta["qp_n"], B), dtype=torch.float64, device=dev),
+                         torch.empty((B,), dtype=torch.int32, device=dev),
+                         torch.empty((2, B), dtype=torch.int32, device=dev)))
+        else:
+            nq, nx = meta["n_robot"], meta["n_virtual"]
+            outs.append((torch.empty((nq, B), dtype=torch.float64, device=dev),
+                         torch.empty((nx, B), dtype=torch.float64, device=dev) if nx else None,
+                         torch.empty((B,), dtype=torch.int32, device=dev)))
+
+    def step(i):
+        t, q, x, y = ins[i % n_sets]
+        ctrl.solve_batch(t, q, x, y, out=outs[i % n_sets])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(warm, 3)):
+        step(i)
+    barrier()
+    # The K timed steps are K launches of the step kernel through the C ABI.  They are captured once
+    # into a CUDA graph and replayed, so that host jitter (8 ranks sharing the box's cores with the
+    # clock samplers) cannot turn a 27 us kernel into a launch-bound loop; same kernels, same inputs.
+    graph = None
+    if os.environ.get("CLIK_BENCH_GRAPH", "1") == "1":
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(steps):
+                    step(i)
+            g.replay()                       # untimed: uploads the graph
+            graph = g
+        except Exception as exc:             # capture not possible: time the plain launch loop
+            sys.stderr.write("bench: CUDA graph capture failed (%s); timing direct launches\n" % exc)
+            graph = None
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    if graph is not None:
+        graph.replay()
+    else:
+        for i in range(steps):
+            step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    return float(tms.item()), n_sets, graph is not None, step
+
+
+def rooflines(meta, is_qp, B, sec_per_step, hbm_peak, hbm_src, fp64_peak, counts):
+    """HBM roofline from the algorithmic bytes; fp64 roofline from the EXECUTED fp64 instruction count
+    (ncu, profiles/r2_ncu_counts.json) when there is one, else from the emitter's algorithmic flops
+    (pinv mode 0 only).  The bound is the roof the kernel sits closer to."""
+    bytes_step = meta["qp_bytes_per_step"] if is_qp else meta["pinv_bytes_per_step"]
+    traffic = None
+    if counts.get("batch") == B and counts.get("dram_bytes") is not None:
+        traffic = counts["dram_bytes"]
+    ach = bytes_step * B / sec_per_step / 1e9
+    hbm = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+           "traffic": traffic, "peak_source": hbm_src, "algorithmic_bytes_per_step": bytes_step}
+    detail = {"hbm": hbm}
+    peak_src = ("measured in this run (DFMA micro-benchmark, clik_measure_fp64_peak; MEASURED_PEAKS.json "
+                "has no fp64 entry)")
+    if counts.get("fp64_inst_per_instance"):
+        # every fp64 instruction (DFMA / DMUL / DADD / DSETP ...) occupies the pipe like one DFMA, so the
+        # executed count x 2 flop-equivalents against the measured DFMA peak is the pipe's utilisation
+        ach_tf = 2.0 * counts["fp64_inst_per_instance"] * B / sec_per_step / 1e12
+        detail["fp64"] = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                          "frac": ach_tf / fp64_peak, "traffic": traffic, "peak_source": peak_src,
+                          "executed_fp64_inst_per_instance": counts["fp64_inst_per_instance"],
+                          "note": "executed fp64 thread-instructions per instance from ncu "
+                                  "(profiles/r2_ncu_counts.json), 2 flop-equivalents each"}
+    if not is_qp:
+        flops = meta["pinv_flops_mode0"]
+        ach_tf = flops * B / sec_per_step / 1e12
+        detail["fp64_algorithmic"] = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak,
+                                      "unit": "TFLOP/s", "frac": ach_tf / fp64_peak, "traffic": traffic,
+                                      "peak_source": peak_src, "algorithmic_flops_per_step": flops,
+                                      "transcendentals_per_step": meta["pinv_eval"]["transcendentals"]}
+    cands = [hbm]
+    if "fp64" in detail:
+        cands.append(detail["fp64"])
+    elif "fp64_algorithmic" in detail:
+        cands.append(detail["fp64_algorithmic"])
+    return max(cands, key=lambda r: r["frac"]), detail
 
 
 def main():
@@ -173,9 +349,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenario", default="ur5_track")
     ap.add_argument("--batch", type=int, default=1 << 20, help="instances per GPU per step")
-    ap.add_argument("--sets", type=int, default=5, help="resident input sets rotated over")
+    ap.add_argument("--sets", type=int, default=0, help="resident input/output sets rotated over (0 = enough for 300 MB)")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs")
+    ap.add_argument("--secondary-only", default="", help="(profiling) run only this secondary scenario's timed loop")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -191,7 +369,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from casclik_b200 import runtime
+    from casclik_b200 import runtime, sharding
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); "
                          "use --impl reference for the CPU baseline")
@@ -204,13 +382,51 @@ def main():
         if os.environ.get("CLIK_NUMA_BIND", "1") == "1":
             # one process per GPU: keep each rank (and the pinned host buffers of its e2e leg) on the
             # socket its GPU hangs off.  Not at N = 1, where the cpu_baseline leg wants every host core.
-            from casclik_b200 import sharding
             numa = sharding.bind_to_device_numa_node(local)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    hbm_peak, hbm_src = _peaks()
+    counts_all = _ncu_counts()
+
+    def secondary_leg(name, batch, mode, cfg, fp64_peak, with_cpu):
+        sc = scenarios.get(name)
+        c = sc.make_controller()
+        c.setup_problem_functions()
+        c.setup_solver()
+        qp = sc.controller == "qp"
+        if mode == "strong":
+            lo, hi = sharding.shard_range(batch, rank, world)
+            Bs = hi - lo
+        else:
+            Bs = batch
+        per = _bytes_per_set(c.kernel_meta, qp, Bs)
+        k = int(max(8, min(100, (3 << 30) // max(per, 1))))          # ~3 GB of algorithmic traffic per leg
+        ms_tot, n_sets, graphed, _ = time_device_resident(torch, dist, c, sc, Bs, k, 3, rank, world, dev,
+                                                          seed_base=2000)
+        total = batch if mode == "strong" else batch * world
+        val = total * k / (ms_tot * 1e-3)
+        out = {"config": cfg, "workload": sc.description, "value": val, "unit": UNIT,
+               "ms_per_step": ms_tot / k, "steps": k, "batch_per_gpu": Bs, "global_batch": total,
+               "scaling": mode, "sets_rotated": n_sets,
+               "gpu_launches": k * _launches_per_step(c.kernel_meta, qp)}
+        if rank == 0:
+            roof, detail = rooflines(c.kernel_meta, qp, Bs, ms_tot * 1e-3 / k, hbm_peak, hbm_src, fp64_peak,
+                                     counts_all.get(name, {}))
+            out["roofline"], out["roofline_detail"] = roof, detail
+            out["launch"] = _launch_info(c, qp)
+            if with_cpu:
+                out["cpu_baseline"], _, _ = CpuPort(sc).measure(batch, seconds_target=6.0)
+        return out
+
+    if args.secondary_only:
+        for name, batch, mode, cfg in SECONDARY:
+            if name == args.secondary_only:
+                print(json.dumps(secondary_leg(name, batch, mode, cfg, 1.0, False)))
+        return
 
     ctrl = scenario.make_controller()
     ctrl.setup_problem_functions()
@@ -220,61 +436,10 @@ def main():
     B = args.batch
     # every rank owns an independent shard (weak scaling: B instances per GPU); no collective
     # on the data path — instances are independent
-    sets = []
-    for s in range(args.sets):
-        inp = scenario.sample(B, seed=1000 * rank + s)
-        sets.append(tuple(None if inp[k] is None else torch.from_numpy(np.ascontiguousarray(inp[k])).to(dev)
-                          for k in ("t", "q", "x", "y")))
-    if is_qp:
-        out = (torch.empty((meta["qp_n"], B), dtype=torch.float64, device=dev),
-               torch.empty((B,), dtype=torch.int32, device=dev),
-               torch.empty((2, B), dtype=torch.int32, device=dev))
-    else:
-        nq, nx = meta["n_robot"], meta["n_virtual"]
-        out = (torch.empty((nq, B), dtype=torch.float64, device=dev),
-               torch.empty((nx, B), dtype=torch.float64, device=dev) if nx else None,
-               torch.empty((B,), dtype=torch.int32, device=dev))
-
-    def step(i):
-        t, q, x, y = sets[i % len(sets)]
-        ctrl.solve_batch(t, q, x, y, out=out)
-
     sampler = ClockSampler(local)
     sampler.start()
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
-    # The K timed steps are K launches of the step kernel through the C ABI.  They are captured once
-    # into a CUDA graph and replayed, so that host jitter (8 ranks sharing the box's cores with the
-    # clock samplers) cannot turn a 29 us kernel into a launch-bound loop; same kernels, same inputs.
-    graph = None
-    if os.environ.get("CLIK_BENCH_GRAPH", "1") == "1":
-        try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for i in range(args.steps):
-                    step(i)
-            g.replay()                       # untimed: uploads the graph
-            graph = g
-        except Exception as exc:             # capture not possible: time the plain launch loop
-            sys.stderr.write("bench: CUDA graph capture failed (%s); timing direct launches\n" % exc)
-            graph = None
-        torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    if graph is not None:
-        graph.replay()
-    else:
-        for i in range(args.steps):
-            step(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
+    ms, n_sets, graphed, step = time_device_resident(torch, dist, ctrl, scenario, B, args.steps, args.warmup,
+                                                     rank, world, dev, min_sets=max(args.sets, 2))
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- end to end through the host-buffer C ABI (pinned host inputs, copies inside) --------------
@@ -327,38 +492,13 @@ def main():
     clocks["note"] = ("sampled every 100 ms from warm-up to the end of the e2e loop (plus up to 3 s "
                       "of extra untimed steps when the run is too short for 4 samples)")
 
+    fp64_peak = runtime.measure_fp64_peak(local) if rank == 0 else 0.0
+    line = None
     if rank == 0:
-        hbm_peak, hbm_src = _peaks()
-        fp64_peak = runtime.measure_fp64_peak(local)
         sec = ms * 1e-3 / args.steps
-        if is_qp:
-            flops, bytes_step = None, meta["qp_bytes_per_step"]
-        else:
-            flops, bytes_step = meta["pinv_flops_mode0"], meta["pinv_bytes_per_step"]
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                tr = json.load(f)
-            if tr.get("scenario") == scenario.name and tr.get("batch") == B:
-                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]   # bytes per launch, from ncu
-        ach_gbs = bytes_step * B / sec / 1e9
-        roof_hbm = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
-                    "algorithmic_bytes_per_step": bytes_step}
-        roof = roof_hbm
-        detail = {"hbm": roof_hbm}
-        if flops:
-            ach_tf = flops * B / sec / 1e12
-            roof_f = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                      "frac": ach_tf / fp64_peak, "traffic": traffic,
-                      "peak_source": "measured in this run (DFMA micro-benchmark, clik_measure_fp64_peak; "
-                                     "MEASURED_PEAKS.json has no fp64 entry)",
-                      "algorithmic_flops_per_step": flops,
-                      "transcendentals_per_step": meta["pinv_eval"]["transcendentals"]}
-            detail["fp64"] = roof_f
-            if roof_f["frac"] >= roof_hbm["frac"]:
-                roof = roof_f
+        roof, detail = rooflines(meta, is_qp, B, sec, hbm_peak, hbm_src, fp64_peak,
+                                 counts_all.get(scenario.name, {}))
+        bytes_step = meta["qp_bytes_per_step"] if is_qp else meta["pinv_bytes_per_step"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -367,11 +507,11 @@ def main():
                        "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": "independent shards, one per GPU, no collective on the data path",
                        "launch_mode": ("%d step-kernel launches replayed from one CUDA graph" % args.steps
-                                       if graph is not None else "direct launches"),
+                                       if graphed else "direct launches"),
                        "host_affinity": ("rank 0 bound to its GPU's NUMA node: %d of %d CPUs" % (len(numa[1]), len(numa[0]))
                                          if numa else "unbound"),
-                       "l2": "rotating %d resident input sets (%d MB total) > 126 MB L2"
-                             % (args.sets, args.sets * bytes_step * B // (1 << 20)),
+                       "l2": "rotating %d resident input + output sets (%d MB of algorithmic traffic in total) "
+                             "> 126 MB L2" % (n_sets, n_sets * bytes_step * B // (1 << 20)),
                        "launch": _launch_info(ctrl, is_qp)},
             "roofline": {k: v for k, v in roof.items()},
             "roofline_detail": detail,
@@ -381,12 +521,31 @@ def main():
                             "kernel reads inputs from / writes results to mapped host memory over PCIe "
                             "inside the timed region (pageable buffers would take the chunked H2D / "
                             "kernel / D2H pipeline instead)"},
-            "gpu_launches": args.steps * (2 if (is_qp and meta.get("qp_split")
-                                                and os.environ.get("CLIK_QP_SPLIT", "1") != "0") else 1),
+            "gpu_launches": args.steps * _launches_per_step(meta, is_qp),
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline and scenario.name == "ur5_track":
-            line["cpu_baseline"], _, _ = cpu_reference(scenario, B)
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"], _, _ = CpuPort(scenario).measure(B, seconds_target=12.0)
+    del step
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, same run, same timing rules ---------------------------------------
+    if not args.no_secondary:
+        secondary = {}
+        for name, batch, mode, cfg in SECONDARY:
+            if name == scenario.name:
+                continue
+            try:
+                secondary[name] = secondary_leg(name, batch, mode, cfg, fp64_peak,
+                                                with_cpu=(world == 1 and not args.no_cpu_baseline))
+            except Exception as exc:          # the headline line must survive a broken secondary leg
+                secondary[name] = {"config": cfg, "error": "%s: %s" % (type(exc).__name__, exc)}
+                if world > 1:
+                    raise
+            torch.cuda.empty_cache()
+        if line is not None:
+            line["secondary"] = secondary
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

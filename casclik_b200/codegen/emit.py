@@ -340,6 +340,7 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
     out.append("// generated by casclik_b200.codegen for skill %r -- do not edit" % label)
     out.append('#include "clik_math.cuh"')
     out.append('#include "clik_pinv.cuh"')
+    out.append('#include "clik_pinv_group.cuh"')
     out.append('#include "clik_qp.cuh"')
     out.append("")
     pre_struct = []
@@ -422,6 +423,10 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         n_static = int(os.environ.get("CLIK_NSTATIC", "0")) or default_static
         n_static = max(1, min(n_static, len(masks)))
         meta["pinv_static_modes"] = n_static
+        # skills with a run-time tail of the activation map: fast pass (static modes) + group pass
+        has_tail = (not unit_sets) and n_static < len(masks)
+        meta["pinv_split"] = has_tail and os.environ.get("CLIK_PINV_SPLIT", "1") == "1"
+        meta["pinv_group"] = meta["pinv_split"] or os.environ.get("CLIK_PINV_GROUP", "0") == "1"
         out.append("  static constexpr int NSTATIC = %d;   // leading modes instantiated on the static path" % n_static)
         out.append(_switch("static_mask", masks[:n_static], ret="unsigned"))
         em = Emitter(pinv.syms.names, const_table, sincos_name)
@@ -564,6 +569,19 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out.append("  clik::pinv_rollout<Skill>(N, ld, steps, dt, t0, t_stride, q, x, y, vmax_q, vmax_x, qdot_last,")
         out.append("                            xdot_last, mode_last, n_failed);")
         out.append("}")
+        if meta.get("pinv_split"):
+            out.append('extern "C" __global__ void %s clik_pinv_fast_kernel(' % bounds)
+            out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
+            out.append("    const double* y, double* qdot, double* xdot, int* mode) {")
+            out.append("  clik::pinv_step<Skill, %d, %d, true>(N, ld, t, t_stride, q, x, y, qdot, xdot, mode);" % (unroll, pf))
+            out.append("}")
+        if meta.get("pinv_group"):
+            # sub-warp mapping (clik_pinv_group.cuh): tail of the fast pass, or whole batches on request
+            out.append('extern "C" __global__ void __launch_bounds__(clik::GroupGeometry<Skill>::BLOCK) clik_pinv_group_kernel(')
+            out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
+            out.append("    const double* y, double* qdot, double* xdot, int* mode, int from_mode, int only_pending) {")
+            out.append("  clik::pinv_group_step<Skill>(N, ld, t, t_stride, q, x, y, qdot, xdot, mode, from_mode, only_pending);")
+            out.append("}")
         if os.environ.get("CLIK_TMA", "0") == "1":
             # opt-in TMA-staged persistent variant (measured slower than the plain kernel)
             out.append('extern "C" __global__ void %s clik_pinv_tma_kernel(' % bounds)
@@ -595,7 +613,8 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
             out.append("    unsigned* active, int max_iter) {")
             out.append("  clik::qp_step_tail<Skill>(N, ld, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
             out.append("}")
-    if qp is not None:
+    qp_rollout = qp is not None and getattr(qp, "emit_rollout", True)
+    if qp_rollout:
         out.append('extern "C" __global__ void __launch_bounds__(%d) clik_qp_rollout_kernel(' % block_threads)
         out.append("    long long N, long long ld, int steps, double dt, const double* t0, int t_stride, double* q, double* x,")
         out.append("    const double* y, double vmax_q, double vmax_x, double* sol_last, int* n_failed, int max_iter) {")
@@ -606,15 +625,19 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
     flags = 0
     if pinv is not None:
         flags |= 2 | (1 if os.environ.get("CLIK_TMA", "0") == "1" else 0)
+        flags |= (32 if meta.get("pinv_group") else 0) | (64 if meta.get("pinv_split") else 0)
     if qp is not None:
-        flags |= 4 | (16 if meta.get("qp_split") else 0)
-    out.append("  // manifest: sizes, unroll, optional-kernel flags (1 pinv TMA, 2 pinv rollout, 4 QP rollout, 16 QP fast + tail pair)")
+        flags |= (4 if qp_rollout else 0) | (16 if meta.get("qp_split") else 0)
+    out.append("  // manifest: sizes, unroll, optional-kernel flags (1 pinv TMA, 2 pinv rollout, 4 QP rollout, 16 QP fast + tail pair,")
+    out.append("  // 32 pinv group kernel, 64 pinv fast kernel); o[16] statically compiled modes, o[17] block size of the group kernel")
     out.append("  o[0] = %d; o[1] = %d; o[2] = %d; o[3] = %d; o[4] = %d; o[5] = %d; o[6] = %d; o[7] = %d;"
                % (nq, nxv, ny, meta["n_modes"], meta["qp_n"], meta["qp_m"], meta.get("pinv_unroll", 1), flags))
     full = (1, 0xffffffff, 0xffffffff, 0xffffffff)
     pm, qm = meta.get("pinv_read_masks", full), meta.get("qp_read_masks", full)
     out.append("  // input rows the kernels read (t, q, x, y bit masks): pinv then QP")
     out.append("  " + " ".join("o[%d] = (int)0x%xu;" % (8 + k, v) for k, v in enumerate(tuple(pm) + tuple(qm))))
+    out.append("  o[16] = %d; o[17] = %s;" % (meta.get("pinv_static_modes", 1),
+                                             "clik::GroupGeometry<Skill>::BLOCK" if meta.get("pinv_group") else "0"))
     out.append("}")
     return "\n".join(out) + "\n", meta
 

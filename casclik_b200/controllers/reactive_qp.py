@@ -212,6 +212,20 @@ class ReactiveQPController(BaseController):
             return None, None
         return self._initial.solve(time_var0, robot_var0, virtual_var0, robot_vel_var0, input_var0)
 
+    def solve_initial_problem_batch(self, time_var0, robot_var0, virtual_var0=None, robot_vel_var0=None,
+                                    input_var0=None, max_iter=None):
+        """solve_initial_problem (reference reactive_qp.py:426-459) for N instances at once: the initial
+        virtual velocities and slack of every scenario of a batch, e.g. to seed the warm start of its first
+        steps.  Arrays are coordinate-major like solve_batch's; robot_vel_var0 / virtual_var0 default to
+        zeros.  Returns (virtual_vel (n_virtual, N) | None, slack (n_slack, N) | None, status (N,))."""
+        if not getattr(self, "_has_initial", None):
+            if getattr(self, "_initial", None) is None:
+                self.setup_initial_problem_solver()
+            if not self._has_initial:
+                return None, None, None
+        return self._initial.solve_batch(time_var0, robot_var0, virtual_var0, robot_vel_var0, input_var0,
+                                         int(max_iter or self.options.get("max_iter", 0) or 0))
+
     # ---- step --------------------------------------------------------------------------------------
     def solve_batch(self, time_var, robot_var, virtual_var=None, input_var=None, warmstart=None,
                     out=None, max_iter=None, warm_active=None, devices=None):

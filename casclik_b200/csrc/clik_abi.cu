@@ -24,6 +24,8 @@
 #include "../../include/clik.h"
 #include "clik_qp.cuh"
 
+namespace clik { constexpr int PINV_TAIL_TILE = 1024; }   // = clik_pinv_group.cuh (not included here: it needs a Skill)
+
 namespace {
 
 thread_local std::string g_err;
@@ -87,8 +89,11 @@ struct ReadMask {
 struct clik_skill {
   clik_skill_desc desc;
   cudaLibrary_t lib = nullptr;
-  KernelInfo pinv, pinv_tma, pinv_rollout, qp, qp_fast, qp_tail, qp_rollout;
+  KernelInfo pinv, pinv_tma, pinv_rollout, pinv_fast, pinv_group, qp, qp_fast, qp_tail, qp_rollout;
   bool qp_split = true;  // CLIK_QP_SPLIT=0: always the single full kernel
+  bool pinv_split = true;     // CLIK_PINV_SPLIT=0: run-time mode tail inside the one kernel (thread mapping)
+  bool pinv_group_all = false;  // CLIK_PINV_GROUP=1: whole batches through the sub-warp mapping (A/B measurements)
+  int n_static = 1;           // statically compiled modes: where the group pass resumes the search
   ReadMask pinv_reads, qp_reads;
   bool use_tma = false;  // opt-in (CLIK_TMA=1): measured slower than the plain kernel, see DESIGN.md
   int sm_count = 0;
@@ -349,7 +354,7 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
   // The image carries its own manifest (clik_sizes_kernel): sizes, which optional kernels it
   // holds, and which input rows its kernels read.  Refuse a descriptor that disagrees.
   clik_status st = CLIK_OK;
-  int hsz[16] = {0};
+  int hsz[24] = {0};
   {
     cudaKernel_t probe;
     cudaError_t pe = cudaLibraryGetKernel(&probe, s->lib, "clik_sizes_kernel");
@@ -383,6 +388,15 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
     if (flags & 1) st = setup_kernel(s, "clik_pinv_tma_kernel", &s->pinv_tma);
     if (const char* e = getenv("CLIK_TMA")) s->use_tma = atoi(e) != 0;
     if (st == CLIK_OK && (flags & 2)) st = setup_kernel(s, "clik_pinv_rollout_kernel", &s->pinv_rollout);
+    if (st == CLIK_OK && (flags & 64)) st = setup_kernel(s, "clik_pinv_fast_kernel", &s->pinv_fast);
+    if (st == CLIK_OK && (flags & 32)) {
+      st = setup_kernel(s, "clik_pinv_group_kernel", &s->pinv_group);
+      s->pinv_group.block = hsz[17] > 0 ? hsz[17] : 64;
+    }
+    if (st == CLIK_OK) s->pinv_fast.unroll = s->pinv.unroll;
+    s->n_static = hsz[16] > 0 ? hsz[16] : 1;
+    if (const char* e = getenv("CLIK_PINV_SPLIT")) s->pinv_split = atoi(e) != 0;
+    if (const char* e = getenv("CLIK_PINV_GROUP")) s->pinv_group_all = atoi(e) != 0;
   }
   if (st == CLIK_OK && desc->has_qp) st = setup_kernel(s, "clik_qp_kernel", &s->qp);
   if (st == CLIK_OK && desc->has_qp) {
@@ -415,7 +429,8 @@ void clik_skill_free(clik_skill* s) {
 clik_status clik_skill_launch_info(const clik_skill* s, int32_t which, int32_t* grid, int32_t* block,
                                    int32_t* regs, int32_t* local_bytes) {
   if (!s) return fail(CLIK_ERR_INVALID, "skill is NULL");
-  const KernelInfo& k = which == 0 ? s->pinv : which == 2 ? s->pinv_tma : which == 3 ? s->qp_fast : which == 4 ? s->qp_tail : s->qp;
+  const KernelInfo& k = which == 0 ? s->pinv : which == 2 ? s->pinv_tma : which == 3 ? s->qp_fast : which == 4 ? s->qp_tail
+                        : which == 5 ? s->pinv_fast : which == 6 ? s->pinv_group : s->qp;
   if (!k.kernel) return fail(CLIK_ERR_INVALID, "skill has no such kernel");
   if (grid) *grid = k.grid;
   if (block) *block = k.block;
@@ -440,7 +455,24 @@ clik_status clik_pinv_step_ld(const clik_skill* s, int64_t N, int64_t ld, const 
   // bulk async copies need 16-byte aligned row segments: even stride and aligned bases
   const bool tma_ok = s->use_tma && s->pinv_tma.kernel && (ld % 2 == 0) && aligned16(t) && aligned16(q) &&
                       aligned16(x) && aligned16(y);
-  if (tma_ok) {
+  const int64_t tiles = (N + clik::PINV_TAIL_TILE - 1) / clik::PINV_TAIL_TILE;
+  if (s->pinv_group_all && s->pinv_group.kernel) {
+    // the whole step in the sub-warp mapping (from mode 0, every instance)
+    int from = 0, pending_only = 0;
+    void* gargs[] = {&n, &l, &t, &ts, &q, &x, &y, &qdot, &xdot, &mode, &from, &pending_only};
+    CK(cudaLaunchKernel((const void*)s->pinv_group.kernel, dim3((unsigned)std::min<int64_t>(tiles, 1 << 20)),
+                        dim3(s->pinv_group.block), gargs, 0, (cudaStream_t)stream));
+  } else if (s->pinv_split && s->pinv_fast.kernel && s->pinv_group.kernel && mode != nullptr) {
+    // two launches: statically compiled modes for every instance (thread mapping, registers), then the
+    // run-time tail of the activation map for the instances they all rejected (sub-warp mapping);
+    // handed over through mode[] (transient value PINV_PENDING)
+    CK(cudaLaunchKernel((const void*)s->pinv_fast.kernel, dim3(grid_for(s->pinv_fast, N)), dim3(s->pinv_fast.block),
+                        args, 0, (cudaStream_t)stream));
+    int from = s->n_static, pending_only = 1;
+    void* gargs[] = {&n, &l, &t, &ts, &q, &x, &y, &qdot, &xdot, &mode, &from, &pending_only};
+    CK(cudaLaunchKernel((const void*)s->pinv_group.kernel, dim3((unsigned)std::min<int64_t>(tiles, 1 << 20)),
+                        dim3(s->pinv_group.block), gargs, 0, (cudaStream_t)stream));
+  } else if (tma_ok) {
     CK(cudaLaunchKernel((const void*)s->pinv_tma.kernel, dim3(balanced_grid(s->pinv_tma, N)),
                         dim3(s->pinv_tma.block), args, 0, (cudaStream_t)stream));
   } else {

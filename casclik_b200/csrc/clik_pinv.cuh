@@ -29,6 +29,10 @@ namespace clik {
 
 enum : int { KIND_EQ = 0, KIND_SET = 1, KIND_VELEQ = 2, KIND_VELSET = 3 };
 
+// Transient value of mode[i] between clik_pinv_fast_kernel (static modes only) and the group pass of
+// clik_pinv_group.cuh, which serves the instances every statically compiled mode rejected.
+constexpr int PINV_PENDING = -2;
+
 template <int A, int B> struct Max { static constexpr int v = A > B ? A : B; };
 
 // Everything S::eval produces for one instance.  Unused members are never touched, so after
@@ -696,7 +700,7 @@ template <class S, int MI> struct StaticDispatch {
 // tests.  Mode 0 and the other frequent modes run on the static register path; the rest use the
 // run-time path on a local-memory copy of the constraint data.  Returns the accepted mode index
 // (-1: none admissible, v = 0, pseudo_inverse.py:551-555).
-template <class S>
+template <class S, bool SPLIT = false>
 __device__ __forceinline__ int solve_instance(const double tv, const double (&qv)[Max<S::NQ, 1>::v],
                                               const double (&xv)[Max<S::NX, 1>::v],
                                               const double (&yv)[Max<S::NY, 1>::v], double (&v)[S::NS]) {
@@ -738,7 +742,10 @@ __device__ __forceinline__ int solve_instance(const double tv, const double (&qv
         break;
       }
     }
-    if constexpr (S::NSTATIC < S::NMODES) {
+    if constexpr (S::NSTATIC < S::NMODES && SPLIT) {
+      // two-launch form: the run-time tail of the activation map is the group pass's job
+      if (accepted < 0) return PINV_PENDING;
+    } else if constexpr (S::NSTATIC < S::NMODES) {
       if (accepted < 0) {
         // the run-time path indexes dynamically: work on copies, keep `d` / `tw` in registers
         PinvData<S> copy = d;
@@ -804,7 +811,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 // the memory latency of instance k+1 hides behind the arithmetic of instance k.
 // PF > 0: every thread also asks L2 for the inputs of the instance PF CTAs ahead (about one wave
 // of resident CTAs), so that the CTA scheduled there later finds its inputs in L2, not in DRAM.
-template <class S, int UNROLL, int PF = 0>
+template <class S, int UNROLL, int PF = 0, bool SPLIT = false>
 __device__ __forceinline__ void pinv_step(long long N, long long ld, const double* __restrict__ t, int t_stride,
                                           const double* __restrict__ q, const double* __restrict__ x,
                                           const double* __restrict__ y, double* __restrict__ qdot,
@@ -829,8 +836,12 @@ __device__ __forceinline__ void pinv_step(long long N, long long ld, const doubl
       const long long i = base + (long long)u * blockDim.x;
       if (i < N) {
         double v[S::NS];
-        const int accepted = solve_instance<S>(tv[u], qv[u], xv[u], yv[u], v);
-        store_instance<S>(ld, i, v, accepted, qdot, xdot, mode);
+        const int accepted = solve_instance<S, SPLIT>(tv[u], qv[u], xv[u], yv[u], v);
+        if (SPLIT && accepted == PINV_PENDING) {
+          __stcs(mode + i, accepted);             // (the split form is only launched with a mode array)
+        } else {
+          store_instance<S>(ld, i, v, accepted, qdot, xdot, mode);
+        }
       }
     }
   }

@@ -78,7 +78,12 @@ void clik_skill_free(clik_skill* skill);
  *   y      [n_input * N]   or NULL when n_input = 0           input_var
  *   qdot   [n_robot * N]   out                                cntrl_rob
  *   xdot   [n_virtual * N] out, or NULL when n_virtual = 0    cntrl_virt
- *   mode   [N] out, may be NULL                               current_mode (-1: none admissible, velocities 0) */
+ *   mode   [N] out, may be NULL                               current_mode (-1: none admissible, velocities 0)
+ * Skills whose activation map has a run-time tail (more than 8 modes on dense sets) run, when `mode` is
+ * given, as two launches: the statically compiled modes for every instance (one thread per instance),
+ * then the rest of the map for the instances those rejected, CLIK_GROUP lanes per instance
+ * (csrc/clik_pinv_group.cuh), handed over through mode[] with the transient value -2.  With mode == NULL
+ * or CLIK_PINV_SPLIT=0: one launch.  CLIK_PINV_GROUP=1 runs whole batches in the sub-warp mapping. */
 clik_status clik_pinv_step(const clik_skill* skill, int64_t N, const double* t, int32_t t_stride,
                            const double* q, const double* x, const double* y, double* qdot,
                            double* xdot, int32_t* mode, void* stream);
@@ -175,7 +180,7 @@ clik_status clik_qp_step_host_multi(const clik_skill* const* skills, int32_t n_s
                                     double* sol, int32_t* status, uint32_t* active, int32_t max_iter);
 
 /* Launch geometry chosen at load time (for reporting). */
-clik_status clik_skill_launch_info(const clik_skill* skill, int32_t which /*0 pinv, 1 qp, 2 pinv TMA-staged, 3 qp fast pass, 4 qp tail pass*/,
+clik_status clik_skill_launch_info(const clik_skill* skill, int32_t which /*0 pinv, 1 qp, 2 pinv TMA-staged, 3 qp fast pass, 4 qp tail pass, 5 pinv fast pass, 6 pinv group pass*/,
                                    int32_t* grid, int32_t* block, int32_t* regs_per_thread,
                                    int32_t* local_bytes_per_thread);
 

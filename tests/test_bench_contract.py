@@ -34,9 +34,15 @@ def test_reference_arm_prints_one_contract_line():
     e2e = d["e2e"]
     assert e2e["value"] == d["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
     assert d["gpu_launches"] == 0
+    # the other BASELINE configs (iiwa multi-task, UR5 QP, Moe-2016 SRMTP + QP) are timed beside it
+    sec = d["secondary"]
+    assert set(sec) == {"iiwa_multitask", "ur5_qp", "ur5_moe2016_pinv", "ur5_moe2016_qp"}
+    for name, leg in sec.items():
+        assert "error" not in leg, (name, leg)
+        assert leg["value"] > 0 and leg["cpu_baseline"]["kind"] == "port" and leg["cpu_baseline"]["cores"] >= 1
 
 
 def test_reference_arm_only_rank_zero_works_under_a_multi_rank_launch():
-    assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2") == []
-    lines = _run({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}, "--gpus", "2")
+    assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2", "--no-secondary") == []
+    lines = _run({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}, "--gpus", "2", "--no-secondary")
     assert len(lines) == 1 and json.loads(lines[0])["n_gpus"] == 2

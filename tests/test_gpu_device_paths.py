@@ -352,3 +352,61 @@ def test_out_buffers_are_validated():
     prev = torch.cuda.current_device()
     ctrl.solve_batch(0.0, inp["q"], None, inp["y"])
     assert torch.cuda.current_device() == prev          # ABI calls leave the caller's device alone
+
+
+@pytest.mark.parametrize("route", ["split", "one_kernel", "group_all"])
+def test_mode_search_routes_agree_on_the_gpu(route, monkeypatch):
+    """The three ways a skill with a run-time mode tail can run — fast pass + sub-warp group pass (default),
+    everything in the one thread-per-instance kernel (CLIK_PINV_SPLIT=0), everything in the sub-warp
+    mapping (CLIK_PINV_GROUP=1, 8 lanes per instance) — against the oracle: same flags, velocities in
+    tolerance.  Skills: iiwa with the closed-form shortcut off (128 modes) and four dense sets (16 modes)."""
+    if route == "one_kernel":
+        monkeypatch.setenv("CLIK_PINV_SPLIT", "0")
+    if route == "group_all":
+        monkeypatch.setenv("CLIK_PINV_GROUP", "1")
+    monkeypatch.setenv("CLIK_UNIT_SETS", "0")
+    sc = scenarios.get("iiwa_multitask")
+    ctrl = sc.make_controller()
+    ctrl.setup_solver()
+    info = ctrl.kernel_meta
+    assert info["pinv_group"] and (info["pinv_split"] == (route != "one_kernel"))
+    inp = _deep_iiwa_inputs(sc, 6000, seed=31)
+    ref_v, ref_mode = oracle_pinv(sc.spec, inp)
+    v, mode = _run_pinv(ctrl, inp)
+    assert (ref_mode >= 29).sum() > 200
+    assert np.array_equal(mode, ref_mode), "mode flags differ in %d instances" % int((mode != ref_mode).sum())
+    assert close(v, ref_v, RTOL, ATOL).all(), np.abs(v - ref_v).max()
+    # mode == NULL (no hand-over array): the one-kernel form is used and gives the same velocities
+    torch = _torch()
+    out = (torch.empty((7, 6000), dtype=torch.float64, device="cuda"), None, None)
+    ctrl.solve_batch(_up(inp["t"]), _up(inp["q"]), None, _up(inp["y"]), out=out)
+    torch.cuda.synchronize()
+    assert close(out[0].cpu().numpy(), ref_v, RTOL, ATOL).all()
+    spec = _dense_sets_skill()
+    c2 = cc.PseudoInverseController(spec)
+    c2.setup_solver()
+    rng = np.random.default_rng(9)
+    N = 30011
+    inp2 = {"t": rng.uniform(0, 5, N), "q": rng.uniform(-0.9, 0.9, (5, N))}
+    ref2, mode2 = oracle_pinv(spec, inp2)
+    v2, m2 = _run_pinv(c2, inp2)
+    assert np.array_equal(m2, mode2) and (mode2 >= 11).sum() > 100
+    err = np.linalg.norm(v2 - ref2, axis=0) / np.maximum(np.linalg.norm(ref2, axis=0), 1e-300)
+    assert close(v2, ref2, RTOL, ATOL).mean() > 0.995 and err[np.isfinite(err)].max() < 1e-8
+
+
+def test_sub_warp_mapping_on_the_benchmark_skills_gpu(monkeypatch):
+    """CLIK_PINV_GROUP=1 on the default builds of the BASELINE skills (the A/B of DESIGN §4): the whole step,
+    modes included, in the 8-lanes-per-instance mapping reproduces the oracle."""
+    monkeypatch.setenv("CLIK_PINV_GROUP", "1")
+    for name, n in (("ur5_track", 5000), ("ur5_moe2016_pinv", 5000), ("iiwa_multitask", 3000)):
+        sc = scenarios.get(name)
+        ctrl = sc.make_controller()
+        ctrl.setup_solver()
+        assert ctrl.kernel_meta["pinv_group"]
+        inp = sc.sample(n, seed=41)
+        ref_v, ref_mode = oracle_pinv(sc.spec, inp)
+        v, mode = _run_pinv(ctrl, inp)
+        assert np.array_equal(mode, ref_mode), name
+        nerr = np.linalg.norm(v - ref_v, axis=0) / np.maximum(np.linalg.norm(ref_v, axis=0), 1e-300)
+        assert close(v, ref_v, RTOL, ATOL).mean() > 0.999 and nerr.max() < 1e-9, (name, nerr.max())

@@ -76,6 +76,43 @@ def test_initial_value_problem_reproduces_the_reference(name):
                 assert np.abs(g - w).max() <= 1e-7 * (1 + np.abs(w).max())
 
 
+@pytest.mark.parametrize("name", QP)
+def test_batched_initial_value_problem_reproduces_the_reference(name):
+    """solve_initial_problem_batch: the initial QP (reactive_qp.py:300-459) lowered through the expression
+    compiler into its own fused kernel, all fixture instances in one launch (device and host ABI), against
+    the slack / virtual velocities the reference's solve_initial_problem produced one at a time."""
+    import torch
+    from test_golden_controllers import VECTORS, initial_args
+    spec, inp, kwargs, outputs = load_case(name)
+    ctrl = cc.ReactiveQPController(spec, **kwargs)
+    ctrl.setup_initial_problem_solver()
+    recs = VECTORS[name]["initial"]
+    K = len(recs)
+    args = [initial_args(spec, inp, VECTORS[name], i)[1] for i in range(K)]
+    t = np.array([a[0] for a in args])
+    q = np.stack([a[1] for a in args], axis=1)
+    x = None if args[0][2] is None else np.stack([a[2] for a in args], axis=1)
+    dq = np.stack([a[3] for a in args], axis=1)
+    y = None if args[0][4] is None else np.stack([a[4] for a in args], axis=1)
+    up = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    virt, slack, status = ctrl.solve_initial_problem_batch(up(t), up(q), up(x), up(dq), up(y))
+    torch.cuda.synchronize()
+    assert bool((status == 0).all())
+    hv, hs, hst = ctrl.solve_initial_problem_batch(t, q, x, dq, y)          # host ABI, same bits
+    for i, ini in enumerate(recs):
+        for got, hgot, want in ((virt, hv, ini["virtual"]), (slack, hs, ini["slack"])):
+            if want is None:
+                assert got is None
+            else:
+                g, w = got[:, i].cpu().numpy(), np.array(want)
+                assert np.abs(g - w).max() <= 1e-7 * (1 + np.abs(w).max()), (name, i)
+                assert np.array_equal(np.asarray(hgot)[:, i], g)
+    # zero robot velocity is the default, as in the reference (:441-442)
+    v0, s0, _ = ctrl.solve_initial_problem_batch(up(t), up(q), up(x), None, up(y))
+    v1, s1, _ = ctrl.solve_initial_problem_batch(up(t), up(q), up(x), up(np.zeros_like(dq)), up(y))
+    assert (s0 is None or torch.equal(s0, s1)) and (v0 is None or torch.equal(v0, v1))
+
+
 @pytest.mark.parametrize("name", sorted(n for n in PINV + QP if "rollout" in
                                         __import__("test_golden_controllers").VECTORS[n]))
 def test_device_rollout_reproduces_the_reference_simulation_loop(name):

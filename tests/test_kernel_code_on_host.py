@@ -48,6 +48,9 @@ static inline double __hiloint2double(int hi, int lo) {
   unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo; double x; std::memcpy(&x, &b, 8); return x; }
 static inline unsigned __activemask() { return 1u; }
 static inline int __any_sync(unsigned, int p) { return p; }
+static inline int __all_sync(unsigned, int p) { return p; }
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+#define CLIK_GROUP 1   // sub-warp mapping with groups of one lane: same code path, one host "thread"
 static inline void __syncthreads() {}
 static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
 using std::fma; using std::fmax; using std::fmin; using std::fabs; using std::sqrt;
@@ -242,6 +245,7 @@ def test_mode_search_variants_agree_with_the_oracle(env, tmp_path, monkeypatch):
     assert np.array_equal(mode, ref_mode)
     assert len(np.unique(ref_mode)) > 40 and ref_mode.max() > 60
     assert close(qdot, ref_v, 1e-9, 1e-12).all(), np.abs(qdot - ref_v).max()
+    _check_split_and_group_passes(lib, ctrl, (t, q, x, y), qdot, mode, ref_v)
 
 
 def test_dense_sets_take_the_dynamic_tail(tmp_path):
@@ -269,6 +273,32 @@ def test_dense_sets_take_the_dynamic_tail(tmp_path):
     ok = close(qdot, ref_v, 1e-9, 1e-12)
     err = np.linalg.norm(qdot - ref_v, axis=0) / np.maximum(np.linalg.norm(ref_v, axis=0), 1e-300)
     assert ok.mean() > 0.995 and err[np.isfinite(err)].max() < 1e-8, (ok.mean(), err.max())
+    _check_split_and_group_passes(lib, ctrl, (t_, q_, None, None), qdot, mode, ref_v)
+
+
+def _check_split_and_group_passes(lib, ctrl, tqxy, qdot_full, mode_full, ref_v):
+    """The two-launch form (clik_pinv_fast_kernel + clik_pinv_group_kernel on what it left pending) and the
+    whole step in the sub-warp mapping (group kernel from mode 0; groups of one lane on the host) against
+    the single full kernel: same flags, velocities equal to rounding."""
+    t, q, x, y = tqxy
+    assert ctrl.kernel_meta["pinv_split"] and ctrl.kernel_meta["pinv_group"]
+    nq, N = q.shape
+    n_static = ctrl.kernel_meta["pinv_static_modes"]
+    v2, m2 = np.full((nq, N), np.nan), np.full(N, -9, dtype=np.int32)
+    head = (ctypes.c_longlong(N), ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y), _p(v2), None, _p(m2))
+    lib.clik_pinv_fast_kernel(*head)
+    pending = m2 == -2
+    assert pending.sum() == (mode_full >= n_static).sum() + (mode_full == -1).sum() and pending.any()
+    assert np.array_equal(m2[~pending], mode_full[~pending]) and np.array_equal(v2[:, ~pending], qdot_full[:, ~pending])
+    lib.clik_pinv_group_kernel(*head, ctypes.c_int(n_static), ctypes.c_int(1))
+    assert np.array_equal(m2, mode_full)
+    scale = np.maximum(np.linalg.norm(ref_v, axis=0), 1e-12)
+    assert (np.linalg.norm(v2 - qdot_full, axis=0) / scale).max() < 1e-8
+    v3, m3 = np.full((nq, N), np.nan), np.full(N, -9, dtype=np.int32)
+    lib.clik_pinv_group_kernel(ctypes.c_longlong(N), ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(q), _p(x), _p(y),
+                               _p(v3), None, _p(m3), ctypes.c_int(0), ctypes.c_int(0))
+    assert np.array_equal(m3, mode_full)
+    assert (np.linalg.norm(v3 - ref_v, axis=0) / scale).max() < 1e-8
 
 
 @pytest.mark.parametrize("seed", range(12))
