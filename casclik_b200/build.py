@@ -157,3 +157,18 @@ def kernel_registers(cubin_path, kernel):
         return None
     m = re.search(r"Used (\d+) registers", log[log.index(key):])
     return int(m.group(1)) if m else None
+
+
+def kernel_stack_bytes(cubin_path, kernel):
+    """Local-memory stack frame (spills + arrays) ptxas reported for `kernel`, in bytes per thread."""
+    import re
+    log_path = cubin_path[:-len(".cubin")] + ".log"
+    if not os.path.exists(log_path):
+        return None
+    with open(log_path) as f:
+        log = f.read()
+    key = "Compiling entry function '%s'" % kernel
+    if key not in log:
+        return None
+    m = re.search(r"(\d+) bytes stack frame", log[log.index(key):])
+    return int(m.group(1)) if m else None

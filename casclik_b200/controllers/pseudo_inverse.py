@@ -111,12 +111,22 @@ class PseudoInverseController(BaseController):
         source, meta = emit_skill(pinv=prog, label=self.skill_spec.label)
         cubin, path = build.compile_cubin(source, tag="pinv_" + self.skill_spec.label)
         regs = build.kernel_registers(path, "clik_pinv_kernel")
-        if regs is not None and regs > 128 and "CLIK_MINBLOCKS" not in os.environ:
-            # large skills (7-DOF pose tasks, many sets) are latency-bound at 2 CTAs/SM: measured
-            # 1.7e9 -> 2.8e9 steps/s for the iiwa scenario with the register cap of 4 CTAs/SM
-            source, meta = emit_skill(pinv=prog, label=self.skill_spec.label, min_blocks=4)
-            cubin, path = build.compile_cubin(source, tag="pinv_" + self.skill_spec.label)
-            meta["register_cap"] = "launch_bounds(128, 4): natural allocation was %d" % regs
+        if regs is not None and regs > 168 and "CLIK_MINBLOCKS" not in os.environ:
+            # Large skills (7-DOF pose tasks, many sets): at the natural allocation only 2 CTAs of 128 fit an
+            # SM.  Capping at 168 registers (3 CTAs/SM) wins while the spills it causes stay small, and loses
+            # when they do not (measured, profiles/r2_ab.txt: iiwa 4-row pose 7.1e9 -> 7.7e9 steps/s with
+            # 368 B of local memory per thread; 9-row stress skill 4.6e9 -> 3.9e9 with 832 B; the round-1
+            # cap of 4 CTAs/SM is behind both since the sincos rewrite freed the local-memory round trip).
+            src3, meta3 = emit_skill(pinv=prog, label=self.skill_spec.label, min_blocks=3)
+            cubin3, path3 = build.compile_cubin(src3, tag="pinv_" + self.skill_spec.label)
+            local3 = build.kernel_stack_bytes(path3, "clik_pinv_kernel")
+            if local3 is not None and local3 <= 512:
+                source, meta, cubin, path = src3, meta3, cubin3, path3
+                meta["register_cap"] = ("launch_bounds(128, 3): natural allocation was %d registers, "
+                                        "%d B local memory under the cap" % (regs, local3))
+            else:
+                meta["register_cap"] = ("none: natural allocation %d registers; the 3-CTA cap would spill %s B"
+                                        % (regs, local3))
         self.kernel_source, self.kernel_meta, self.cubin_path = source, meta, path
         self._nx, self._ny = prog.n_virt, prog.n_in
         self._cubin = cubin

@@ -369,7 +369,7 @@ def test_mode_search_routes_agree_on_the_gpu(route, monkeypatch):
     ctrl = sc.make_controller()
     ctrl.setup_solver()
     info = ctrl.kernel_meta
-    assert info["pinv_group"] and (info["pinv_split"] == (route != "one_kernel"))
+    assert info["pinv_split"] == (route != "one_kernel") and info["pinv_group"] == (route != "one_kernel")
     inp = _deep_iiwa_inputs(sc, 6000, seed=31)
     ref_v, ref_mode = oracle_pinv(sc.spec, inp)
     v, mode = _run_pinv(ctrl, inp)
