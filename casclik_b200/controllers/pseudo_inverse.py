@@ -243,21 +243,37 @@ class PseudoInverseController(BaseController):
         if getattr(self, "_cubin", None) is None:
             raise RuntimeError("call setup_problem_functions() / setup_solver() before solve()")
         nq = spec.n_robot_var
-        q = as_vector(robot_var, nq, "robot_var").reshape(nq, 1)
+        q = np.ascontiguousarray(as_vector(robot_var, nq, "robot_var"))
         use_virt = virtual_var is not None and spec._has_virtual
         x = None
         if self._nx:
             if spec._has_virtual and virtual_var is None:
                 raise ValueError("the skill depends on virtual_var: a value is required")
-            x = (as_vector(virtual_var, self._nx, "virtual_var") if virtual_var is not None
-                 else np.zeros(self._nx)).reshape(self._nx, 1)
+            x = np.ascontiguousarray(as_vector(virtual_var, self._nx, "virtual_var") if virtual_var is not None
+                                     else np.zeros(self._nx))
         y = None
         if self._ny:
             if input_var is None:
                 raise ValueError("the skill depends on input_var: a value is required")
-            y = as_vector(input_var, self._ny, "input_var").reshape(self._ny, 1)
-        t = np.array([float(time_var)])
-        qdot, xdot, mode = self.solve_batch(t, q, x, y)
-        self.current_mode = int(mode[0])
-        cntrl_virt = dm_column(xdot[:, 0]) if use_virt else None
-        return dm_column(qdot[:, 0]), cntrl_virt, None
+            y = np.ascontiguousarray(as_vector(input_var, self._ny, "input_var"))
+        # one instance: straight to the single-instance ABI entry (a page-locked mapped slot inside the
+        # library; no batch plumbing, no allocation) — the call a notebook makes in its control loop
+        one = getattr(self, "_one", None)
+        if one is None or one["nq"] != nq:
+            import ctypes
+            buf = {"nq": nq, "qdot": np.empty(nq), "xdot": np.empty(max(self._nx, 1)),
+                   "mode": np.zeros(1, dtype=np.int32)}
+            buf["qdot_p"] = ctypes.c_void_p(buf["qdot"].ctypes.data)
+            buf["xdot_p"] = ctypes.c_void_p(buf["xdot"].ctypes.data) if self._nx else None
+            buf["mode_p"] = ctypes.c_void_p(buf["mode"].ctypes.data)
+            one = self._one = buf
+        import ctypes
+        skill = self._skill()
+        runtime.check(skill._lib.clik_pinv_solve_one(
+            skill.handle, ctypes.c_double(float(time_var)), ctypes.c_void_p(q.ctypes.data),
+            ctypes.c_void_p(x.ctypes.data) if x is not None else None,
+            ctypes.c_void_p(y.ctypes.data) if y is not None else None,
+            one["qdot_p"], one["xdot_p"], one["mode_p"]))
+        self.current_mode = int(one["mode"][0])
+        cntrl_virt = dm_column(one["xdot"][:self._nx]) if use_virt else None
+        return dm_column(one["qdot"]), cntrl_virt, None

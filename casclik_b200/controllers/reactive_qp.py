@@ -313,18 +313,18 @@ class ReactiveQPController(BaseController):
             raise RuntimeError("call setup_problem_functions() / setup_solver() before solve()")
         nrob, nvirt, nslack = spec.n_robot_var, spec.n_virtual_var, spec.n_slack_var
         has_virtual = spec._has_virtual
-        q = as_vector(robot_var, nrob, "robot_var").reshape(nrob, 1)
+        q = np.ascontiguousarray(as_vector(robot_var, nrob, "robot_var")).reshape(nrob, 1)
         x = None
         if self._nxv:
             if has_virtual and virtual_var is None:
                 raise ValueError("the skill depends on virtual_var: a value is required")
-            x = (as_vector(virtual_var, self._nxv, "virtual_var") if virtual_var is not None
-                 else np.zeros(self._nxv)).reshape(self._nxv, 1)
+            x = np.ascontiguousarray(as_vector(virtual_var, self._nxv, "virtual_var") if virtual_var is not None
+                                     else np.zeros(self._nxv)).reshape(self._nxv, 1)
         y = None
         if self._ny:
             if input_var is None:
                 raise ValueError("the skill depends on input_var: a value is required")
-            y = as_vector(input_var, self._ny, "input_var").reshape(self._ny, 1)
+            y = np.ascontiguousarray(as_vector(input_var, self._ny, "input_var")).reshape(self._ny, 1)
         ws_rob = warmstart_robot_vel_var is not None
         ws_virt = warmstart_virtual_vel_var is not None and has_virtual
         ws_slack = warmstart_slack_var is not None and nslack > 0
@@ -338,8 +338,25 @@ class ReactiveQPController(BaseController):
             if nslack:
                 parts.append(as_vector(warmstart_slack_var, nslack, "warmstart_slack_var")
                              if ws_slack else np.zeros(nslack))
-            warm = np.concatenate(parts).reshape(-1, 1)
-        sol, status, active = self.solve_batch(np.array([float(time_var)]), q, x, y, warmstart=warm)
+            warm = np.ascontiguousarray(np.concatenate(parts).reshape(-1, 1))
+        # one instance: the single-instance ABI entry (page-locked mapped slot inside the library)
+        import ctypes
+        one = getattr(self, "_one", None)
+        if one is None or one["qn"] != self._qn:
+            buf = {"qn": self._qn, "sol": np.empty(self._qn), "status": np.zeros(1, dtype=np.int32),
+                   "active": np.zeros(2, dtype=np.uint32)}
+            for k in ("sol", "status", "active"):
+                buf[k + "_p"] = ctypes.c_void_p(buf[k].ctypes.data)
+            one = self._one = buf
+        skill = self._skill()
+        mi = int(self.options.get("max_iter", 0) or 0)
+        runtime.check(skill._lib.clik_qp_solve_one(
+            skill.handle, ctypes.c_double(float(time_var)), ctypes.c_void_p(q.ctypes.data),
+            ctypes.c_void_p(x.ctypes.data) if x is not None else None,
+            ctypes.c_void_p(y.ctypes.data) if y is not None else None,
+            ctypes.c_void_p(warm.ctypes.data) if warm is not None else None,
+            one["sol_p"], one["status_p"], one["active_p"], mi))
+        sol, status, active = one["sol"].reshape(-1, 1).copy(), one["status"], one["active"].reshape(2, 1)
         if int(status[0]) != runtime.QP_SOLVED:
             raise RuntimeError("QP %s" % ("is infeasible" if int(status[0]) == runtime.QP_INFEASIBLE
                                           else "hit the iteration cap"))

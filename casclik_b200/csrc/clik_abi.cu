@@ -97,8 +97,14 @@ struct clik_skill {
   ReadMask pinv_reads, qp_reads;
   bool use_tma = false;  // opt-in (CLIK_TMA=1): measured slower than the plain kernel, see DESIGN.md
   int sm_count = 0;
-  std::mutex mu;  // guards scratch
+  std::mutex mu;  // guards scratch and the single-instance slot
   Scratch scratch;
+  // single-instance calls (the reference API's solve()): one page-locked, device-mapped slot holding the
+  // inputs and outputs of one instance + a stream, so a call is: fill the slot, one launch, one wait
+  double* one_host = nullptr;
+  double* one_dev = nullptr;
+  size_t one_doubles = 0;
+  cudaStream_t one_stream = nullptr;
 };
 
 namespace {
@@ -418,6 +424,8 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
 void clik_skill_free(clik_skill* s) {
   if (!s) return;
   DeviceGuard guard(s->desc.device);
+  if (s->one_host) cudaFreeHost(s->one_host);
+  if (s->one_stream) cudaStreamDestroy(s->one_stream);
   for (int i = 0; i < NSLOTS; ++i) {
     if (s->scratch.dev[i]) cudaFree(s->scratch.dev[i]);
     if (s->scratch.stream[i]) cudaStreamDestroy(s->scratch.stream[i]);
@@ -751,6 +759,100 @@ clik_status clik_qp_step_host_multi(const clik_skill* const* skills, int32_t n_s
   return run_sharded(skills, n_skills, N, [&](clik_skill* s, int64_t lo, int64_t cnt) {
     return qp_host_range(s, N, lo, cnt, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);
   });
+}
+
+// ---- single instance (PseudoInverseController.solve / ReactiveQPController.solve as the reference calls
+// them, one robot state at a time): HOST pointers to the vectors of ONE instance.  The instance goes
+// through a page-locked slot mapped into the device address space: no allocation, no staging copies, no
+// pointer queries per call — fill, launch on the skill's own stream, wait, read.
+static clik_status one_slot(clik_skill* s, size_t doubles) {
+  if (!s->one_stream) CK(cudaStreamCreateWithFlags(&s->one_stream, cudaStreamNonBlocking));
+  if (s->one_doubles < doubles) {
+    if (s->one_host) CK(cudaFreeHost(s->one_host));
+    s->one_host = nullptr;
+    s->one_doubles = 0;
+    CK(cudaHostAlloc((void**)&s->one_host, doubles * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable));
+    CK(cudaHostGetDevicePointer((void**)&s->one_dev, s->one_host, 0));
+    s->one_doubles = doubles;
+  }
+  return CLIK_OK;
+}
+
+clik_status clik_pinv_solve_one(const clik_skill* cs, double t, const double* q, const double* x, const double* y,
+                                double* qdot, double* xdot, int32_t* mode) {
+  clik_skill* s = const_cast<clik_skill*>(cs);
+  if (!s || !q || !qdot) return fail(CLIK_ERR_INVALID, "NULL argument");
+  if (!s->pinv.kernel) return fail(CLIK_ERR_INVALID, "skill was built without the pinv kernel");
+  const clik_skill_desc& d = s->desc;
+  if (d.n_virtual > 0 && (!x || !xdot)) return fail(CLIK_ERR_INVALID, "skill has virtual_var: x and xdot are required");
+  if (d.n_input > 0 && !y) return fail(CLIK_ERR_INVALID, "skill reads input_var: y is required");
+  ON_DEVICE(d.device);
+  std::lock_guard<std::mutex> lock(s->mu);
+  const int nq = d.n_robot, nx = d.n_virtual, ny = d.n_input;
+  clik_status st = one_slot(s, (size_t)(2 + 2 * nq + 2 * nx + ny + 2));
+  if (st != CLIK_OK) return st;
+  double* h = s->one_host;
+  // slot: t | q | x | y | qdot | xdot | mode (as one double-sized cell)
+  h[0] = t;
+  std::memcpy(h + 1, q, sizeof(double) * nq);
+  if (nx) std::memcpy(h + 1 + nq, x, sizeof(double) * nx);
+  if (ny) std::memcpy(h + 1 + nq + nx, y, sizeof(double) * ny);
+  const size_t o_in = 1 + nq + nx + ny;
+  double* dv = s->one_dev;
+  long long n = 1, l = 1;
+  int ts = 0;
+  const double *dt = dv, *dq = dv + 1, *dx = nx ? dv + 1 + nq : nullptr, *dy = ny ? dv + 1 + nq + nx : nullptr;
+  double *dqd = dv + o_in, *dxd = nx ? dv + o_in + nq : nullptr;
+  int* dm = (int*)(dv + o_in + nq + nx);
+  void* args[] = {&n, &l, &dt, &ts, &dq, &dx, &dy, &dqd, &dxd, &dm};
+  CK(cudaLaunchKernel((const void*)s->pinv.kernel, dim3(1), dim3(32), args, 0, s->one_stream));
+  CK(cudaStreamSynchronize(s->one_stream));
+  std::memcpy(qdot, h + o_in, sizeof(double) * nq);
+  if (nx) std::memcpy(xdot, h + o_in + nq, sizeof(double) * nx);
+  if (mode) *mode = *(const int*)(h + o_in + nq + nx);
+  return CLIK_OK;
+}
+
+clik_status clik_qp_solve_one(const clik_skill* cs, double t, const double* q, const double* x, const double* y,
+                              const double* x0, double* sol, int32_t* status, uint32_t* active, int32_t max_iter) {
+  clik_skill* s = const_cast<clik_skill*>(cs);
+  if (!s || !q || !sol) return fail(CLIK_ERR_INVALID, "NULL argument");
+  if (!s->qp.kernel) return fail(CLIK_ERR_INVALID, "skill was built without the QP kernel");
+  const clik_skill_desc& d = s->desc;
+  if (d.n_virtual > 0 && !x) return fail(CLIK_ERR_INVALID, "skill has virtual_var: x is required");
+  if (d.n_input > 0 && !y) return fail(CLIK_ERR_INVALID, "skill reads input_var: y is required");
+  ON_DEVICE(d.device);
+  std::lock_guard<std::mutex> lock(s->mu);
+  const int nq = d.n_robot, nx = d.n_virtual, ny = d.n_input, qn = d.qp_n;
+  clik_status st = one_slot(s, (size_t)(1 + nq + nx + ny + 2 * qn + 3));
+  if (st != CLIK_OK) return st;
+  double* h = s->one_host;
+  // slot: t | q | x | y | x0 | sol | status, active_up, active_lo (three int cells in two doubles)
+  h[0] = t;
+  std::memcpy(h + 1, q, sizeof(double) * nq);
+  if (nx) std::memcpy(h + 1 + nq, x, sizeof(double) * nx);
+  if (ny) std::memcpy(h + 1 + nq + nx, y, sizeof(double) * ny);
+  const size_t o_x0 = 1 + nq + nx + ny, o_sol = o_x0 + qn, o_int = o_sol + qn;
+  if (x0) std::memcpy(h + o_x0, x0, sizeof(double) * qn);
+  double* dv = s->one_dev;
+  long long n = 1, l = 1;
+  int ts = 0;
+  int mi = max_iter > 0 ? max_iter : 10 * (d.qp_n + d.qp_m);
+  const double *dt = dv, *dq = dv + 1, *dx = nx ? dv + 1 + nq : nullptr, *dy = ny ? dv + 1 + nq + nx : nullptr;
+  const double* dx0 = x0 ? dv + o_x0 : nullptr;
+  const unsigned* da0 = nullptr;
+  double* dsol = dv + o_sol;
+  int* dst = (int*)(dv + o_int);
+  unsigned* dact = (unsigned*)(dv + o_int) + 1;      // active[0], active[ld = 1]
+  void* args[] = {&n, &l, &dt, &ts, &dq, &dx, &dy, &dx0, &da0, &dsol, &dst, &dact, &mi};
+  // one instance: the single full kernel (prediction + iteration in one launch)
+  CK(cudaLaunchKernel((const void*)s->qp.kernel, dim3(1), dim3(32), args, 0, s->one_stream));
+  CK(cudaStreamSynchronize(s->one_stream));
+  std::memcpy(sol, h + o_sol, sizeof(double) * qn);
+  const int* hi = (const int*)(h + o_int);
+  if (status) *status = hi[0];
+  if (active) { active[0] = (uint32_t)hi[1]; active[1] = (uint32_t)hi[2]; }
+  return CLIK_OK;
 }
 
 clik_status clik_measure_fp64_peak(int32_t device, int32_t iters, double* tflops) {

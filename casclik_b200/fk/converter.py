@@ -195,6 +195,28 @@ def _affine_times(A, B):
     return cs.SX._wrap(out)
 
 
+def _tip_frame_joint(S, arg, kind, axis):
+    """Axis direction and a point on the axis of one joint in TIP coordinates, from the suffix transform
+    S = (joint frame -> tip): a_b = R_s' a, o_b = -R_s' p_s.  Ingredients of dag.ChainBlock."""
+    a = _axis_unit(axis)
+    s = S._a
+    ab, ob = [], []
+    for k in range(3):
+        acc_a, acc_o = dag.ZERO, dag.ZERO
+        for i in range(3):
+            acc_a = dag.add(acc_a, dag.mul(s[i, k], dag.const(float(a[i]))))
+            acc_o = dag.add(acc_o, dag.mul(s[i, k], s[i, 3]))
+        ab.append(acc_a)
+        ob.append(dag.neg(acc_o))
+    return (arg.nodes()[0], kind, ab, ob)
+
+
+def _register_block(T, joints):
+    """Tell the AD layer that T = [R p] is a kinematic chain (closed-form tip-frame partials)."""
+    t = T._a
+    dag.register_chain_block(dag.ChainBlock([[t[i, k] for k in range(4)] for i in range(3)], joints))
+
+
 def quaternion_product(p, q):
     """Hamilton product, [x y z w] layout, symbolic or numeric column vectors."""
     p = p if isinstance(p, cs.GenericMatrixCommon) else cs.DM(p)
@@ -247,14 +269,18 @@ def from_joint_list(path):
 
     # homogeneous transform, accumulated tip -> root with split factors
     U = cs.SX.eye(4)
+    joints = []
     for j in reversed(path):
         if j.type in ("revolute", "continuous"):
             U = _affine_times(rotation_axis_angle(j.axis, q[index[j.name]]), U)
+            joints.append(_tip_frame_joint(U, q[index[j.name]], "revolute", j.axis))
         elif j.type == "prismatic":
             U = _affine_times(translation_axis(j.axis, q[index[j.name]]), U)
+            joints.append(_tip_frame_joint(U, q[index[j.name]], "prismatic", j.axis))
         elif j.type != "fixed":
             raise NotImplementedError("joint type %r" % j.type)
         U = _affine_times(cs.SX(origin_matrix(j.xyz, j.rpy)), U)
+    _register_block(U, joints)
 
     # (dual) quaternion, accumulated root -> tip
     Q = cs.DM([0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0])
@@ -297,6 +323,7 @@ def from_denavit_hartenberg(joint_angles, link_lengths, link_offsets, link_twist
     n = len(link_lengths)
     q = cs.SX.sym("q", n)
     U = cs.SX.eye(4)
+    joints = []
     for i in reversed(range(n)):
         theta = q[i] if isinstance(joint_angles[i], str) else joint_angles[i]
         d = q[i] if isinstance(link_offsets[i], str) else link_offsets[i]
@@ -307,7 +334,12 @@ def from_denavit_hartenberg(joint_angles, link_lengths, link_offsets, link_twist
         B[0, 3] = link_lengths[i]
         B[2, 3] = d
         U = _affine_times(B, U)
+        if isinstance(link_offsets[i], str):
+            joints.append(_tip_frame_joint(U, q[i], "prismatic", (0, 0, 1)))
         U = _affine_times(rotation_axis_angle((0, 0, 1), theta), U)
+        if isinstance(joint_angles[i], str):
+            joints.append(_tip_frame_joint(U, q[i], "revolute", (0, 0, 1)))
+    _register_block(U, joints)
     names = list(joint_names) if joint_names is not None else ["joint_%d" % i for i in range(n)]
     return {
         "joint_names": names,

@@ -34,6 +34,7 @@ EXPORTS = (
     "clik_qp_rollout", "clik_qp_dense",
     "clik_pinv_step_host", "clik_qp_step_host", "clik_skill_launch_info",
     "clik_pinv_step_ld", "clik_qp_step_ld", "clik_pinv_step_host_multi", "clik_qp_step_host_multi",
+    "clik_pinv_solve_one", "clik_qp_solve_one",
     "clik_measure_fp64_peak", "clik_flush_l2", "clik_device_count", "clik_abi_version",
     "clik_last_error",
 )
@@ -81,6 +82,10 @@ def load_library():
     lib.clik_qp_step_host_multi.restype = i32
     lib.clik_qp_step_host_multi.argtypes = [ctypes.POINTER(vp), i32, i64, vp, i32, vp, vp, vp, vp, vp, vp,
                                             vp, vp, i32]
+    lib.clik_pinv_solve_one.restype = i32
+    lib.clik_pinv_solve_one.argtypes = [vp, ctypes.c_double, vp, vp, vp, vp, vp, vp]
+    lib.clik_qp_solve_one.restype = i32
+    lib.clik_qp_solve_one.argtypes = [vp, ctypes.c_double, vp, vp, vp, vp, vp, vp, vp, i32]
     lib.clik_pinv_rollout.restype = i32
     lib.clik_pinv_rollout.argtypes = [vp, i64, i32, ctypes.c_double, vp, i32, vp, vp, vp,
                                       ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, vp]

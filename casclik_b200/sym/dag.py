@@ -477,7 +477,205 @@ def jacobian(outputs: Sequence[Node], wrt: Sequence[Node]) -> List[List[Node]]:
         if not s.is_sym:
             raise ValueError("jacobian: differentiation variable must be purely symbolic")
         cols.append(forward(outputs, {s.id: ONE}))
-    return [[cols[j][i] for j in range(len(wrt))] for i in range(len(outputs))]
+    rows = [[cols[j][i] for j in range(len(wrt))] for i in range(len(outputs))]
+    if _AD_MODE[0] == "auto" and _chain_blocks and len(wrt) > 1:
+        for i, o in enumerate(outputs):
+            alt = _reverse_row(o, wrt)
+            # keep the smaller graph; the primal `o` is in both so that shared work is not counted against either
+            if alt is not None and graph_cost(alt + [o]) < graph_cost(rows[i] + [o]):
+                rows[i] = alt
+    return rows
+
+
+# ----------------------------------------------------------------------------------------------
+# kinematic-chain blocks and reverse-mode rows
+# ----------------------------------------------------------------------------------------------
+# A forward-kinematics transform T(q) = [R p] of an n-joint chain is the one place where forward-mode
+# AD is badly matched to the problem: every joint direction drags its own 3x3 tangent through the rest
+# of the chain, although d T / d q_j has a closed form in the TIP frame,
+#     dR = R [a_j]x dq_j ,   dp = R (o_j x a_j) dq_j        (revolute; a_j = joint axis, o_j = a point on it,
+#     dR = 0 ,               dp = R a_j dq_j                  (prismatic)        both in tip coordinates)
+# whose ingredients a_j, o_j come out of the SUFFIX transforms the chain product computes anyway.  The FK
+# front-end registers that structure as a ChainBlock; `jacobian` then offers, per scalar output row, a
+# second derivation: reverse-mode AD down to the block's entries (adjoints F_R, F_p), pulled back
+# through the block as   d e / d q_j = a_j . (kappa(R' F_R) + (R' F_p) x o_j),   and keeps whichever of
+# the two graphs is smaller.  Orientation-error rows (||R_des' R - I||_F and the like) shrink several
+# fold; position rows usually stay forward.  Both derivations are exact, they differ by rounding only.
+
+class ChainBlock(object):
+    """T: 3x4 nested list of nodes [R | p]; joints: list of (arg node, "revolute" | "prismatic",
+    a_b (3 nodes), o_b (3 nodes)) with axis / axis point in tip coordinates."""
+
+    def __init__(self, T, joints):
+        self.T = [list(r) for r in T]
+        self.joints = [(a, k, list(ab), list(ob)) for a, k, ab, ob in joints]
+
+    def entries(self):
+        return [n for r in self.T for n in r]
+
+    def all_nodes(self):
+        out = self.entries()
+        for a, _, ab, ob in self.joints:
+            out += [a] + ab + ob
+        return out
+
+
+_chain_blocks: Dict[int, "ChainBlock"] = {}
+_AD_MODE = ["auto"]        # "auto": smaller of forward / reverse-through-blocks per row; "forward": forward only
+
+
+class ad_mode(object):
+    """Context manager: `with dag.ad_mode("forward"):` forces plain forward-mode Jacobians (the tests'
+    oracle bridge uses it, so the oracle never shares the block pull-back with the product)."""
+
+    def __init__(self, mode):
+        if mode not in ("auto", "forward"):
+            raise ValueError(mode)
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = _AD_MODE[0]
+        _AD_MODE[0] = self.mode
+
+    def __exit__(self, *exc):
+        _AD_MODE[0] = self.prev
+
+
+def register_chain_block(block: "ChainBlock"):
+    for n in block.entries():
+        if n.op not in ("const", "sym"):
+            _chain_blocks[n.id] = block
+
+
+class _NoReverseRule(Exception):
+    pass
+
+
+def _acc(adj, node, val):
+    if node.op == "const" or val is ZERO:
+        return
+    cur = adj.get(node.id)
+    adj[node.id] = val if cur is None else add(cur, val)
+
+
+def _reverse_to_leaves(output: Node, cut: Dict[int, "ChainBlock"]):
+    """Adjoints d output / d leaf for the leaves of output's graph, where symbols and the entries of
+    registered chain blocks are leaves.  -> ({leaf id: adjoint node}, {leaf id: leaf node})"""
+    seen: Dict[int, Node] = {}
+    stack = [output]
+    while stack:
+        n = stack.pop()
+        if n.id in seen:
+            continue
+        seen[n.id] = n
+        if n.id in cut or n.op in ("const", "sym"):
+            continue
+        stack.extend(n.args)
+    adj: Dict[int, Node] = {output.id: ONE}
+    leaves: Dict[int, Node] = {}
+    for nid in sorted(seen, reverse=True):
+        n = seen[nid]
+        g = adj.get(nid)
+        if g is None or n.op == "const":
+            continue
+        if n.id in cut or n.op == "sym":
+            leaves[nid] = n
+            continue
+        a = n.args
+        op = n.op
+        if op == "add":
+            _acc(adj, a[0], g)
+            _acc(adj, a[1], g)
+        elif op == "sub":
+            _acc(adj, a[0], g)
+            _acc(adj, a[1], neg(g))
+        elif op == "neg":
+            _acc(adj, a[0], neg(g))
+        elif op == "mul":
+            _acc(adj, a[0], mul(g, a[1]))
+            _acc(adj, a[1], mul(g, a[0]))
+        elif op == "div":
+            q = div(g, a[1])
+            _acc(adj, a[0], q)
+            _acc(adj, a[1], neg(mul(q, n)))
+        elif op == "sqrt":
+            _acc(adj, a[0], div(g, mul(TWO, n)))
+        elif op == "sin":
+            _acc(adj, a[0], mul(g, cos(a[0])))
+        elif op == "cos":
+            _acc(adj, a[0], neg(mul(g, sin(a[0]))))
+        elif op == "exp":
+            _acc(adj, a[0], mul(g, n))
+        elif op == "log":
+            _acc(adj, a[0], div(g, a[0]))
+        else:
+            raise _NoReverseRule(op)      # piecewise / rarely used ops: the row stays forward-mode
+    return adj, leaves
+
+
+def _block_pullback(block: "ChainBlock", adj) -> List[Node]:
+    """d e / d (joint argument j) from the adjoints of the block's entries (missing = zero)."""
+    R = [block.T[i][:3] for i in range(3)]
+    FR = [[adj.get(block.T[i][k].id, ZERO) if block.T[i][k].op != "const" else ZERO for k in range(3)] for i in range(3)]
+    Fp = [adj.get(block.T[i][3].id, ZERO) if block.T[i][3].op != "const" else ZERO for i in range(3)]
+
+    def dot3(u, v):
+        return add(add(mul(u[0], v[0]), mul(u[1], v[1])), mul(u[2], v[2]))
+
+    # K = R' F_R ; kappa = (K32 - K23, K13 - K31, K21 - K12) ; g = R' F_p
+    K = [[dot3([R[0][i], R[1][i], R[2][i]], [FR[0][k], FR[1][k], FR[2][k]]) for k in range(3)] for i in range(3)]
+    kappa = [sub(K[2][1], K[1][2]), sub(K[0][2], K[2][0]), sub(K[1][0], K[0][1])]
+    g = [dot3([R[0][i], R[1][i], R[2][i]], Fp) for i in range(3)]
+    out = []
+    for _, kind, ab, ob in block.joints:
+        if kind == "prismatic":
+            out.append(dot3(g, ab))
+        else:
+            gxo = [sub(mul(g[1], ob[2]), mul(g[2], ob[1])), sub(mul(g[2], ob[0]), mul(g[0], ob[2])),
+                   sub(mul(g[0], ob[1]), mul(g[1], ob[0]))]
+            out.append(dot3(ab, [add(kappa[0], gxo[0]), add(kappa[1], gxo[1]), add(kappa[2], gxo[2])]))
+    return out
+
+
+_OP_COST = {"add": 1, "sub": 1, "mul": 1, "div": 4, "sqrt": 4, "sin": 10, "cos": 10}
+
+
+def graph_cost(nodes: Sequence[Node]) -> int:
+    return sum(_OP_COST.get(n.op, 0 if n.op in ("const", "sym", "neg") else 2) for n in topo(nodes))
+
+
+def _reverse_row(output: Node, wrt: Sequence[Node]):
+    """Row of the Jacobian by reverse mode through the registered chain blocks, or None."""
+    blocks = {}
+    for n in topo([output]):
+        b = _chain_blocks.get(n.id)
+        if b is not None:
+            blocks[id(b)] = b
+    if not blocks:
+        return None
+    cut = {n.id: b for b in blocks.values() for n in b.entries() if n.op not in ("const", "sym")}
+    try:
+        adj, leaves = _reverse_to_leaves(output, cut)
+    except _NoReverseRule:
+        return None
+    # total derivative w.r.t. a requested symbol s: direct adjoint + sum over joint arguments of
+    # (pull-back to that argument) x d argument / d s   (arguments are the symbols themselves unless the
+    # FK function was called with expressions)
+    args, pulls = [], []
+    for b in blocks.values():
+        pb = _block_pullback(b, adj)
+        for (arg, _, _, _), pj in zip(b.joints, pb):
+            args.append(arg)
+            pulls.append(pj)
+    row = []
+    for s_ in wrt:
+        t = adj.get(s_.id, ZERO) if s_.id in leaves else ZERO
+        darg = forward(args, {s_.id: ONE}) if args else []
+        for pj, da in zip(pulls, darg):
+            if da is not ZERO and pj is not ZERO:
+                t = add(t, mul(pj, da))
+        row.append(t)
+    return row
 
 
 # ----------------------------------------------------------------------------------------------
@@ -496,6 +694,15 @@ _CTOR = {
 def substitute(outputs: Sequence[Node], mapping: Dict[int, Node]) -> List[Node]:
     """Replace symbols (by id) with nodes and rebuild (re-simplifying on the way)."""
     order = topo(outputs)
+    # chain blocks whose entries are being rebuilt travel with them (their axis data is substituted too)
+    touched = {}
+    for n in order:
+        b = _chain_blocks.get(n.id)
+        if b is not None:
+            touched[id(b)] = b
+    extra = [m for b in touched.values() for m in b.all_nodes()]
+    if extra:
+        order = topo(list(outputs) + extra)
     new: Dict[int, Node] = {}
     for n in order:
         if n.op == "const":
@@ -508,6 +715,11 @@ def substitute(outputs: Sequence[Node], mapping: Dict[int, Node]) -> List[Node]:
                 new[n.id] = n
             else:
                 new[n.id] = _CTOR[n.op](*args)
+    for b in touched.values():
+        nb = ChainBlock([[new[m.id] for m in r] for r in b.T],
+                        [(new[a.id], k, [new[m.id] for m in ab], [new[m.id] for m in ob]) for a, k, ab, ob in b.joints])
+        if any(x is not y for x, y in zip(nb.all_nodes(), b.all_nodes())):
+            register_chain_block(nb)
     return [new[o.id] for o in outputs]
 
 

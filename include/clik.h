@@ -163,6 +163,16 @@ clik_status clik_qp_step_host(const clik_skill* skill, int64_t N, const double* 
                               const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
                               int32_t max_iter);
 
+/* One instance, HOST pointers to its vectors (t by value): the reference's solve() call itself
+ * (pseudo_inverse.py:512-556, reactive_qp.py:461-528), synchronous.  The instance travels through a
+ * page-locked device-mapped slot owned by the skill (no allocation, copy engine or pointer query per call):
+ * launch + wait, ~10 us.   active[2] = {upper mask, lower mask}. */
+clik_status clik_pinv_solve_one(const clik_skill* skill, double t, const double* q, const double* x,
+                                const double* y, double* qdot, double* xdot, int32_t* mode);
+clik_status clik_qp_solve_one(const clik_skill* skill, double t, const double* q, const double* x,
+                              const double* y, const double* x0, double* sol, int32_t* status,
+                              uint32_t* active, int32_t max_iter);
+
 /* One host batch over several GPUs of the box: `skills[k]` is the same cubin loaded on device k
  * (clik_skill_load with desc.device = k); the batch is cut into n_skills contiguous shards (sizes differ
  * by at most one, shard k = [k*N/n .. )), each shard runs on its device from its own host thread (zero

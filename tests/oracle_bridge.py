@@ -42,7 +42,14 @@ def _num(matrix, vals, N):
 
 
 def blocks_from_skill(spec, t, q, x=None, y=None):
-    """-> (list of oracle Blocks in priority order, n_state)."""
+    """-> (list of oracle Blocks in priority order, n_state).  Jacobians are plain forward-mode AD
+    (dag.ad_mode("forward")): the oracle never takes the kinematic-chain pull-back the product's lowering
+    may choose, so kernel-vs-oracle parity also cross-checks the two derivations."""
+    with dag.ad_mode("forward"):
+        return _blocks_from_skill(spec, t, q, x, y)
+
+
+def _blocks_from_skill(spec, t, q, x=None, y=None):
     N = q.shape[1]
     t = np.broadcast_to(np.asarray(t, dtype=np.float64).reshape(-1), (N,)) if np.ndim(t) else \
         np.full((N,), float(t))

@@ -84,3 +84,68 @@ def test_fixture_qp_minimisers_match_a_second_solver(name):
         assert abs(obj_s - obj_g) <= 1e-9 * (1 + abs(obj_g))
         xo, lam, st = orc.solve_qp_single(gh, gA[i], glb[i], gub[i])
         assert st == 0 and np.abs(xo - xs).max() <= 1e-8 * (1 + np.abs(xs).max())
+
+
+@pytest.mark.parametrize("name", sorted(n for n in VECTORS if VECTORS[n]["controller"] == "pinv"))
+def test_lowered_program_matches_the_sympy_rebuild(name):
+    """What the emitter turns into CUDA — codegen.lower.PinvProgram, whose Jacobian rows may come from the
+    kinematic-chain pull-back (sym.dag: reverse mode through registered FK blocks) instead of forward AD —
+    evaluated with the NumPy interpreter against the sympy pins."""
+    from casclik_b200.codegen import PinvProgram
+    from casclik_b200.controllers import PseudoInverseController
+    spec, inp, kwargs, outputs = load_case(name)
+    opts = PseudoInverseController(spec, **kwargs).options
+    prog = PinvProgram(spec, opts)
+    pin = _pin(name)
+    K = pin["n_instances"]
+    by_label = {c["label"]: c for c in pin["constraints"]}
+    vals = {prog.syms.t[0].id: inp["t"][:K]}
+    for arr, nodes in (("q", prog.syms.q), ("x", prog.syms.x), ("y", prog.syms.y)):
+        for k, s in enumerate(nodes):
+            vals[s.id] = inp[arr][k, :K]
+    for b in prog.blocks:
+        p = by_label[b["label"]]
+        nodes = [n for r in b["J"] for n in r] + list(b["e"]) + list(b["jt"])
+        got = [np.broadcast_to(np.asarray(v, dtype=float), (K,)) for v in dag.evaluate(nodes, vals)]
+        m, ns = b["rows"], prog.ns
+        for i in range(K):
+            row = p["instances"][i]
+            J = np.array([[got[r * ns + c][i] for c in range(ns)] for r in range(m)])
+            e = np.array([got[m * ns + r][i] for r in range(m)])
+            jt = np.array([got[m * ns + m + r][i] for r in range(m)])
+            wantJ = np.array(row["J"])
+            assert np.abs(J - wantJ).max() <= 1e-13 * (1 + np.abs(wantJ).max()), (name, b["label"], i)
+            assert np.abs(e - np.array(row["e"])[:, 0]).max() <= 2e-14 * (1 + np.abs(e).max())
+            assert np.abs(jt - np.array(row["Jt"])[:, 0]).max() <= 2e-14 * (1 + np.abs(jt).max())
+
+
+def test_chain_pullback_is_chosen_for_the_orientation_row_and_shrinks_the_program():
+    """iiwa pose task: the ||R_des' R - I||_F row takes the reverse / tip-frame derivation (963 -> 393 eval
+    flops); position rows and the UR5 skills keep forward AD (it is the smaller graph there)."""
+    from casclik_b200 import scenarios
+    from casclik_b200.codegen import PinvProgram
+    sc = scenarios.get("iiwa_multitask")
+    ctrl = sc.make_controller()
+    auto = PinvProgram(sc.spec, ctrl.options)
+    with dag.ad_mode("forward"):
+        fwd = PinvProgram(sc.spec, ctrl.options)
+    ja = [n for b in auto.blocks for r in b["J"] for n in r]
+    jf = [n for b in fwd.blocks for r in b["J"] for n in r]
+    assert dag.graph_cost(ja) < 0.6 * dag.graph_cost(jf)
+    pose_a, pose_f = auto.blocks[-1]["J"], fwd.blocks[-1]["J"]
+    assert all(a is f for a, f in zip(pose_a[0], pose_f[0]))            # position row: same (forward) nodes
+    assert any(a is not f for a, f in zip(pose_a[3], pose_f[3]))        # orientation row: different derivation
+    inp = sc.sample(50, seed=2)
+    vals = {auto.syms.t[0].id: inp["t"]}
+    for arr, nodes in (("q", auto.syms.q), ("y", auto.syms.y)):
+        for k, s in enumerate(nodes):
+            vals[s.id] = inp[arr][k]
+    va = np.array([np.broadcast_to(v, (50,)) for v in dag.evaluate(ja, vals)])
+    vf = np.array([np.broadcast_to(v, (50,)) for v in dag.evaluate(jf, vals)])
+    assert np.abs(va - vf).max() < 1e-13
+    u = scenarios.get("ur5_track")
+    cu = u.make_controller()
+    with dag.ad_mode("forward"):
+        uf = PinvProgram(u.spec, cu.options)
+    ua = PinvProgram(u.spec, cu.options)
+    assert all(a is f for ra, rf in zip(ua.blocks[0]["J"], uf.blocks[0]["J"]) for a, f in zip(ra, rf))
