@@ -111,22 +111,28 @@ class PseudoInverseController(BaseController):
         source, meta = emit_skill(pinv=prog, label=self.skill_spec.label)
         cubin, path = build.compile_cubin(source, tag="pinv_" + self.skill_spec.label)
         regs = build.kernel_registers(path, "clik_pinv_kernel")
-        if regs is not None and regs > 168 and "CLIK_MINBLOCKS" not in os.environ:
-            # Large skills (7-DOF pose tasks, many sets): at the natural allocation only 2 CTAs of 128 fit an
-            # SM.  Capping at 168 registers (3 CTAs/SM) wins while the spills it causes stay small, and loses
-            # when they do not (measured, profiles/r2_ab.txt: iiwa 4-row pose 7.1e9 -> 7.7e9 steps/s with
-            # 368 B of local memory per thread; 9-row stress skill 4.6e9 -> 3.9e9 with 832 B; the round-1
-            # cap of 4 CTAs/SM is behind both since the sincos rewrite freed the local-memory round trip).
-            src3, meta3 = emit_skill(pinv=prog, label=self.skill_spec.label, min_blocks=3)
-            cubin3, path3 = build.compile_cubin(src3, tag="pinv_" + self.skill_spec.label)
-            local3 = build.kernel_stack_bytes(path3, "clik_pinv_kernel")
-            if local3 is not None and local3 <= 512:
-                source, meta, cubin, path = src3, meta3, cubin3, path3
-                meta["register_cap"] = ("launch_bounds(128, 3): natural allocation was %d registers, "
-                                        "%d B local memory under the cap" % (regs, local3))
+        if regs is not None and regs > 128 and "CLIK_MINBLOCKS" not in os.environ:
+            # Large skills (7-DOF pose tasks, many sets) are latency-bound at the 2-3 CTAs of 128 threads per
+            # SM their natural register allocation allows.  A register cap buys occupancy and costs spills;
+            # it wins while the spills stay small (measured, profiles/r2_ab.txt + r2_ab2.txt: iiwa pose skill
+            # 166 regs natural 1.20e10 steps/s, cap 128 regs / 200 B local 1.33e10, cap 96 regs / 360 B 1.08e10;
+            # before the chain pull-back shrank it: 208 regs natural 7.1e9, cap 168 / 368 B 7.7e9, cap 128 /
+            # 520 B 6.6e9; 9-row stress skill: 255 regs natural 4.6e9, cap 168 / 832 B 3.9e9).  Rule: the
+            # highest occupancy among 3 and 4 CTAs/SM whose local-memory frame stays within 400 B.
+            natural = regs
+            for min_blocks, cap in ((4, 128), (3, 168)):
+                if natural <= cap:
+                    continue
+                src_c, meta_c = emit_skill(pinv=prog, label=self.skill_spec.label, min_blocks=min_blocks)
+                cubin_c, path_c = build.compile_cubin(src_c, tag="pinv_" + self.skill_spec.label)
+                local_c = build.kernel_stack_bytes(path_c, "clik_pinv_kernel")
+                if local_c is not None and local_c <= 400:
+                    source, meta, cubin, path = src_c, meta_c, cubin_c, path_c
+                    meta["register_cap"] = ("launch_bounds(128, %d): natural allocation was %d registers, "
+                                            "%d B local memory under the cap" % (min_blocks, natural, local_c))
+                    break
             else:
-                meta["register_cap"] = ("none: natural allocation %d registers; the 3-CTA cap would spill %s B"
-                                        % (regs, local3))
+                meta["register_cap"] = "none: natural allocation %d registers; a cap would spill more than 400 B" % natural
         self.kernel_source, self.kernel_meta, self.cubin_path = source, meta, path
         self._nx, self._ny = prog.n_virt, prog.n_in
         self._cubin = cubin

@@ -62,8 +62,9 @@ class ConicSolver(object):
                                                    lb, ub, x0a)
         if status[0] != runtime.QP_SOLVED:
             raise RuntimeError("conic solver %s: QP %s" % (
-                self.name, "is infeasible" if status[0] == runtime.QP_INFEASIBLE
-                else "hit the iteration cap"))
+                self.name, {runtime.QP_INFEASIBLE: "is infeasible",
+                            runtime.QP_INVALID: "has non-finite data or a non-finite solution (is H positive?)"
+                            }.get(int(status[0]), "hit the iteration cap")))
         xs = x[0]
         return {"x": cs.DM(xs.reshape(-1, 1)), "cost": cs.DM(0.5 * float(xs @ (np.diag(H) * xs))),
                 "active_upper": int(active[0, 0]), "active_lower": int(active[0, 1])}

@@ -158,6 +158,12 @@ class ReactiveQPController(BaseController):
         """Emit + compile + load the fused QP kernel; also exposes H_func / A_func / Blb_func /
         Bub_func (host-evaluated `cs.Function`s, for inspection as in the reference :283-298)."""
         prog = self._program()
+        bad = [k for k, n in enumerate(prog.h) if n.is_const and not (n.val > 0.0 and np.isfinite(n.val))]
+        if bad:
+            # (the reference hands a semidefinite H to qpOASES, which copes when the constraints pin x
+            # down; the GPU solver works in sqrt(H)-scaled variables and needs a strictly convex cost)
+            raise ValueError("QP cost weights must be positive and finite: entries %s of the diagonal of H "
+                             "(mu*robot weights; mu*virtual weights; mu + slack weights) are not" % bad)
         source, meta = emit_skill(qp=prog, label=self.skill_spec.label)
         cubin, path = build.compile_cubin(source, tag="qp_" + self.skill_spec.label)
         self.kernel_source, self.kernel_meta, self.cubin_path = source, meta, path
@@ -358,8 +364,9 @@ class ReactiveQPController(BaseController):
             one["sol_p"], one["status_p"], one["active_p"], mi))
         sol, status, active = one["sol"].reshape(-1, 1).copy(), one["status"], one["active"].reshape(2, 1)
         if int(status[0]) != runtime.QP_SOLVED:
-            raise RuntimeError("QP %s" % ("is infeasible" if int(status[0]) == runtime.QP_INFEASIBLE
-                                          else "hit the iteration cap"))
+            raise RuntimeError("QP %s" % {runtime.QP_INFEASIBLE: "is infeasible",
+                                          runtime.QP_INVALID: "has non-finite data or a non-finite solution "
+                                                              "(NaN input?)"}.get(int(status[0]), "hit the iteration cap"))
         xs = sol[:, 0]
         hdiag = self._h_const if self._h_const is not None else np.asarray(
             self.H_func(*self._numeric_args(time_var, q, x, y)).toarray()).diagonal()

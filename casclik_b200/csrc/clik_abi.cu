@@ -159,8 +159,9 @@ clik_status check_common(const clik_skill* s, int64_t N, const double* t, const 
 }
 
 // ---- dense QP kernel (the cs.conic call for numeric H/A/lb/ub) --------------------------------------
-constexpr int DENSE_NX = 16, DENSE_M = 32;
-
+// Capacity tiers of the dense solver (working storage is per-thread local memory, so the larger tier is
+// only instantiated for problems that need it).
+template <int NXC, int MC>
 __global__ void clik_qp_dense_kernel(long long N, int nx, int m, const double* __restrict__ h,
                                      const double* __restrict__ A, const double* __restrict__ lb,
                                      const double* __restrict__ ub, const double* __restrict__ x0,
@@ -168,7 +169,7 @@ __global__ void clik_qp_dense_kernel(long long N, int nx, int m, const double* _
                                      unsigned* __restrict__ active, int max_iter) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-    double Al[DENSE_M * DENSE_NX], lbl[DENSE_M], ubl[DENSE_M], hl[DENSE_NX], xs[DENSE_NX], x0l[DENSE_NX];
+    double Al[MC * NXC], lbl[MC], ubl[MC], hl[NXC], xs[NXC], x0l[NXC];
     for (int j = 0; j < nx; ++j) hl[j] = h[(long long)j * N + i];
     for (int r = 0; r < m; ++r) {
       lbl[r] = lb[(long long)r * N + i];
@@ -177,13 +178,17 @@ __global__ void clik_qp_dense_kernel(long long N, int nx, int m, const double* _
     }
     if (x0) for (int j = 0; j < nx; ++j) x0l[j] = x0[(long long)j * N + i];
     unsigned mu, ml;
-    int st = clik::qp_dual_active_set<DENSE_NX, DENSE_M>(nx, m, Al, lbl, ubl, hl, x0 ? x0l : nullptr,
-                                                         xs, &mu, &ml, max_iter);
+    int st = clik::qp_dual_active_set<NXC, MC>(nx, m, Al, lbl, ubl, hl, x0 ? x0l : nullptr, xs, &mu, &ml, max_iter);
+    bool finite = true;
+    for (int j = 0; j < nx; ++j) finite = finite && (fabs(xs[j]) < INFINITY);
+    if (st == clik::QP_OK && !finite) st = clik::QP_INVALID;
     for (int j = 0; j < nx; ++j) sol[(long long)j * N + i] = xs[j];
     if (status) status[i] = st;
     if (active) { active[i] = mu; active[N + i] = ml; }
   }
 }
+constexpr int DENSE_NX = 16, DENSE_M = 32;          // tier 1
+constexpr int DENSE_NX2 = 32, DENSE_M2 = 64;        // tier 2 (32 KB of local memory per thread)
 
 // ---- measurement helpers -------------------------------------------------------------------------------
 __global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
@@ -575,18 +580,23 @@ clik_status clik_qp_dense(int32_t device, int64_t N, int32_t nx, int32_t m, cons
                           double* sol, int32_t* status, uint32_t* active, int32_t max_iter,
                           void* stream) {
   if (N < 0 || nx <= 0 || m < 0) return fail(CLIK_ERR_INVALID, "bad sizes");
-  if (nx > DENSE_NX || m > DENSE_M)
-    return fail(CLIK_ERR_INVALID, "clik_qp_dense supports nx <= %d, m <= %d", DENSE_NX, DENSE_M);
+  if (nx > DENSE_NX2 || m > DENSE_M2)
+    return fail(CLIK_ERR_INVALID, "clik_qp_dense supports nx <= %d, m <= %d (got %d x %d)", DENSE_NX2, DENSE_M2, m, nx);
   if (N == 0) return CLIK_OK;
   if (!h || (m > 0 && (!A || !lb || !ub)) || !sol) return fail(CLIK_ERR_INVALID, "NULL argument");
   ON_DEVICE(device);
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  const int block = 64;
-  int grid = (int)std::min<int64_t>((N + block - 1) / block, (int64_t)sms * 8);
+  const bool big = nx > DENSE_NX || m > DENSE_M;
+  const int block = big ? 32 : 64;
+  int grid = (int)std::min<int64_t>((N + block - 1) / block, (int64_t)sms * (big ? 2 : 8));
   int mi = max_iter > 0 ? max_iter : 10 * (nx + m);
-  clik_qp_dense_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(N, nx, m, h, A, lb, ub, x0, sol,
-                                                                 status, active, mi);
+  if (big)
+    clik_qp_dense_kernel<DENSE_NX2, DENSE_M2><<<grid, block, 0, (cudaStream_t)stream>>>(N, nx, m, h, A, lb, ub, x0, sol,
+                                                                                     status, active, mi);
+  else
+    clik_qp_dense_kernel<DENSE_NX, DENSE_M><<<grid, block, 0, (cudaStream_t)stream>>>(N, nx, m, h, A, lb, ub, x0, sol,
+                                                                                   status, active, mi);
   CK(cudaGetLastError());
   return CLIK_OK;
 }

@@ -27,7 +27,17 @@
 
 namespace clik {
 
-enum : int { QP_OK = 0, QP_MAXITER = 1, QP_INFEASIBLE = 2, QP_PENDING = 3 /* transient: between the fast and the tail pass */ };
+enum : int { QP_OK = 0, QP_MAXITER = 1, QP_INFEASIBLE = 2, QP_PENDING = 3 /* transient: between the fast and the tail pass */,
+             QP_INVALID = 4 /* non-finite problem data or solution (NaN inputs, non-positive cost weight) */ };
+
+// A solution containing NaN / inf is never reported as solved (a zero cost weight makes 1/sqrt(h) infinite,
+// a NaN input poisons every comparison of the iteration, which then "finds no violated row").
+template <int N> __device__ __forceinline__ bool all_finite(const double (&x)[N]) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < N; ++j) ok = ok && (fabs(x[j]) < INFINITY);
+  return ok;
+}
 
 // NXM / MM: compile-time capacities; nx / m: actual sizes (compile-time constants when inlined
 // into a fused skill kernel).  A is row-major m x nx and is overwritten with the scaled rows.
@@ -838,7 +848,7 @@ __device__ __forceinline__ void qp_instance(long long ld, long long i, const dou
     // predicts the working set from any guess, or none; when the prediction certifies itself its
     // face optimum is the answer and the iteration below is skipped
     bool solved = false;
-    if (S::QP_CRASH && !parked) solved = crash_guess<S>(d, &wu, &wl, xs) && S::QP_CRASH_FINAL;
+    if (S::QP_CRASH && !parked) solved = crash_guess<S>(d, &wu, &wl, xs) && S::QP_CRASH_FINAL && all_finite(xs);
     st = solved ? QP_OK : QP_MAXITER;
     mu = wu;
     ml = wl;
@@ -868,6 +878,7 @@ __device__ __forceinline__ void qp_instance(long long ld, long long i, const dou
     st = qp_dual_active_set<S::QN, S::QM>(S::QN, S::QM, d.A, d.lb, d.ub, d.h, nullptr, xs, &mu, &ml,
                                           max_iter);
   }
+  if (st == QP_OK && !all_finite(xs)) st = QP_INVALID;
   for (int j = 0; j < S::QN; ++j) __stcs(sol + (long long)j * ld + i, xs[j]);
   if (status != nullptr) status[i] = st;
   if (active != nullptr) {
@@ -950,7 +961,7 @@ __device__ __forceinline__ void qp_rollout(long long N, long long ld, int steps,
         S::eval_qps(tv, qv, xv, yv, d);
         unsigned wu = mu, wl = ml;
         bool solved = false;            // previous step's set -> this step's (usually one pass)
-        if (S::QP_CRASH) solved = crash_guess<S>(d, &wu, &wl, xs) && S::QP_CRASH_FINAL;
+        if (S::QP_CRASH) solved = crash_guess<S>(d, &wu, &wl, xs) && S::QP_CRASH_FINAL && all_finite(xs);
         st = solved ? QP_OK : QP_MAXITER;
         if (solved) { mu = wu; ml = wl; }
 #pragma unroll 1
@@ -968,6 +979,7 @@ __device__ __forceinline__ void qp_rollout(long long N, long long ld, int steps,
         st = qp_dual_active_set<S::QN, S::QM>(S::QN, S::QM, d.A, d.lb, d.ub, d.h, nullptr, xs, &mu, &ml,
                                               max_iter);
       }
+      if (st == QP_OK && !all_finite(xs)) st = QP_INVALID;
       if (st != QP_OK) {
         ++failed;
         for (int j = 0; j < S::QN; ++j) xs[j] = 0.0;

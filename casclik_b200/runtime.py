@@ -15,7 +15,7 @@ _c_int32_p = ctypes.POINTER(ctypes.c_int32)
 _c_uint32_p = ctypes.POINTER(ctypes.c_uint32)
 
 ABI_VERSION = 2
-QP_SOLVED, QP_MAXITER, QP_INFEASIBLE = 0, 1, 2
+QP_SOLVED, QP_MAXITER, QP_INFEASIBLE, QP_INVALID = 0, 1, 2, 4
 
 
 class ClikError(RuntimeError):

@@ -521,7 +521,8 @@ class ChainBlock(object):
 
 
 _chain_blocks: Dict[int, "ChainBlock"] = {}
-_AD_MODE = ["auto"]        # "auto": smaller of forward / reverse-through-blocks per row; "forward": forward only
+import os as _os
+_AD_MODE = [_os.environ.get("CLIK_AD_MODE", "auto")]        # "auto": smaller of forward / reverse-through-blocks per row; "forward": forward only
 
 
 class ad_mode(object):

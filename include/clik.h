@@ -45,6 +45,7 @@ typedef enum {
 #define CLIK_QP_SOLVED 0
 #define CLIK_QP_MAXITER 1
 #define CLIK_QP_INFEASIBLE 2
+#define CLIK_QP_INVALID 4 /* non-finite data or solution (NaN input, non-positive cost weight); 3 is internal */
 
 /* Sizes of a compiled skill; must match the constants baked into the cubin (checked at load). */
 typedef struct {
@@ -145,7 +146,8 @@ clik_status clik_qp_rollout(const clik_skill* skill, int64_t N, int32_t steps, d
 /* The conic call itself, `solver(h=H, a=A, lba=lb, uba=ub[, x0=])` (reactive_qp.py:493), for N
  * numeric problems of one shape: min 1/2 x' diag(h) x, lb <= A x <= ub.
  *   h [nx * N], A [(m * nx) * N] row-major per instance (entry (r, c) at A[(r*nx + c)*N + i]),
- *   lb, ub [m * N].  Limits: nx <= 16, m <= 32.  +-inf bounds are allowed. */
+ *   lb, ub [m * N].  Limits: nx <= 32, m <= 64 (two capacity tiers: up to 16 x 32 and up to 32 x 64; the
+ *   working set is reported for the first 32 rows).  +-inf bounds are allowed. */
 clik_status clik_qp_dense(int32_t device, int64_t N, int32_t nx, int32_t m, const double* h,
                           const double* A, const double* lb, const double* ub, const double* x0,
                           double* sol, int32_t* status, uint32_t* active, int32_t max_iter,

@@ -298,3 +298,41 @@ def test_two_launch_split_equals_the_single_kernel(monkeypatch):
         for ta, tb in zip(a, b):
             assert torch.equal(ta, tb)
     assert int(outs["1"][0][1].abs().sum()) == 0          # every status final (0), none left pending
+
+
+def test_non_finite_data_is_reported_not_returned_as_solved():
+    """NaN inputs / a zero weight used to come back with status 0 and NaN velocities."""
+    torch = _torch()
+    sc = scenarios.get("ur5_qp")
+    ctrl = sc.make_controller()
+    ctrl.setup_solver()
+    inp = sc.sample(64, seed=3)
+    inp["q"][2, 5] = np.nan
+    inp["y"][0, 9] = np.inf
+    sol, status, _ = _solve_device(ctrl, inp)
+    assert status[5] == runtime.QP_INVALID and status[9] != runtime.QP_SOLVED
+    ok = np.ones(64, dtype=bool)
+    ok[[5, 9]] = False
+    assert np.all(status[ok] == 0) and np.isfinite(sol[:, ok]).all()
+    with pytest.raises(RuntimeError):
+        ctrl.solve(0.0, inp["q"][:, 5], input_var=inp["y"][:, 5])
+    with pytest.raises(ValueError):
+        bad = cc.ReactiveQPController(sc.spec, robot_var_weights=[1.0, 1.0, 0.0, 1.0, 1.0, 1.0])
+        bad.setup_problem_functions(load=False)
+    # dense conic entry: zero weight -> status 4, never a silent NaN; and the second capacity tier (24 x 40)
+    from casclik_b200.controllers.qp_solver import ConicSolver
+    solver = ConicSolver("solver", "qpoases", {}, {})
+    rng = np.random.default_rng(0)
+    h = np.ones((3, 4)); h[1, 2] = 0.0
+    A = rng.normal(size=(3, 5, 4)); lb = -np.ones((3, 5)); ub = np.ones((3, 5))
+    x, st, _ = solver.solve_dense_batch(h, A, lb, ub)
+    assert st[0] == 0 and st[2] == 0 and st[1] == runtime.QP_INVALID
+    nx, m, N = 24, 40, 6
+    h2 = rng.uniform(0.5, 2.0, (N, nx)); A2 = rng.normal(size=(N, m, nx))
+    c = rng.normal(size=(N, m)); lb2, ub2 = c - 0.3, c + 0.3
+    lb2[:, 20:], ub2[:, 20:] = -1e10, 1e10                       # 20 binding-ish rows, 20 free
+    x2, st2, _ = solver.solve_dense_batch(h2, A2, lb2, ub2)
+    assert np.all(st2 == 0)
+    for i in range(N):
+        xo, lam, so = orc.solve_qp_single(h2[i], A2[i], lb2[i], ub2[i], max_iter=2000)
+        assert so == 0 and np.abs(x2[i] - xo).max() < 1e-7 * (1 + np.abs(xo).max())
