@@ -319,14 +319,15 @@ def _switch(name, values, ret="int"):
             % (ret, name, body))
 
 
-def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks=None):
+def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks=None, qp_fast_min_blocks=None):
     """-> (source text, meta dict).  `pinv`: PinvProgram or None, `qp`: QpProgram or None.
     Tuning knobs (also settable through the environment for experiments): CLIK_BLOCK,
     CLIK_MINBLOCKS, CLIK_CONSTBANK (1), CLIK_FAST_SINCOS (1)."""
     if block_threads is None:
         block_threads = int(os.environ.get("CLIK_BLOCK", "128"))
+    env_min_blocks = int(os.environ.get("CLIK_MINBLOCKS", "0"))
     if min_blocks is None:
-        min_blocks = int(os.environ.get("CLIK_MINBLOCKS", "0"))
+        min_blocks = env_min_blocks
     const_table = [] if os.environ.get("CLIK_CONSTBANK", "1") == "1" else None
     sincos_name = "clik::sincos_fast" if os.environ.get("CLIK_FAST_SINCOS", "1") == "1" else "sincos"
     ref = pinv if pinv is not None else qp
@@ -347,6 +348,7 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
     struct_at = len(out)
     out.append("struct Skill {")
     out.append("  static constexpr int NQ = %d, NX = %d, NY = %d, NS = %d;" % (nq, nxv, ny, nq + nxv))
+    out.append("  static constexpr int BLOCK = %d;   // threads per CTA of the step kernels" % block_threads)
     sig = ("const double t, const double (&q)[%d], const double (&x)[%d], const double (&y)[%d]"
            % (max(nq, 1), max(nxv, 1), max(ny, 1)))
 
@@ -512,6 +514,10 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
                        ("true" if os.environ.get("CLIK_QP_CRASH_FINAL", "1") == "1" else "false"))
             crash_final = os.environ.get("CLIK_QP_CRASH_FINAL", "1") == "1" and os.environ.get("CLIK_QP_CRASH", "1") == "1"
             meta["qp_split"] = crash_final and os.environ.get("CLIK_QP_SPLIT", "1") == "1"
+            out.append("  static constexpr bool QP_CRASH_SINGLE = %s;   // one-row-per-pass prediction passes before the iteration" %
+                       ("true" if os.environ.get("CLIK_QP_CRASH_SINGLE", "1") == "1" else "false"))
+            out.append("  static constexpr int QP_FAST_PASSES = %d;   // prediction passes in the fast launch (the tail continues)" %
+                       int(os.environ.get("CLIK_QP_FAST_PASSES", "4")))
             out.append("  static constexpr bool QP_EQ_START = %s;" %
                        ("true" if os.environ.get("CLIK_QP_EQ_START", "0") == "1" else "false"))
             out.append(_switch("dense_row", qp.dense_rows or [0]))
@@ -562,7 +568,10 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         meta["pinv_prefetch_ctas"] = pf
         out.append("  clik::pinv_step<Skill, %d, %d>(N, ld, t, t_stride, q, x, y, qdot, xdot, mode);" % (unroll, pf))
         out.append("}")
-        out.append('extern "C" __global__ void %s clik_pinv_rollout_kernel(' % bounds)
+        # (the rollout kernel keeps its state across steps in registers: the step kernel's occupancy cap,
+        # chosen from the step kernel's spill size, does not transfer to it)
+        rbounds = "__launch_bounds__(%d%s)" % (block_threads, (", %d" % env_min_blocks) if env_min_blocks else "")
+        out.append('extern "C" __global__ void %s clik_pinv_rollout_kernel(' % rbounds)
         out.append("    long long N, long long ld, int steps, double dt, const double* t0, int t_stride, double* q, double* x,")
         out.append("    const double* y, double vmax_q, double vmax_x, double* qdot_last, double* xdot_last,")
         out.append("    int* mode_last, int* n_failed) {")
@@ -601,7 +610,10 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out.append("}")
         if meta.get("qp_split"):
             # fast pass (working-set prediction only) + tail pass (full solver on what it left pending)
-            out.append('extern "C" __global__ void __launch_bounds__(%d) clik_qp_fast_kernel(' % block_threads)
+            fmin = qp_fast_min_blocks if qp_fast_min_blocks is not None else int(os.environ.get("CLIK_QP_FAST_MINBLOCKS", "0"))
+            meta["qp_fast_min_blocks"] = fmin
+            out.append('extern "C" __global__ void __launch_bounds__(%d%s) clik_qp_fast_kernel(' % (
+                block_threads, (", %d" % fmin) if fmin else ""))
             out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
             out.append("    const double* y, const double* x0, const unsigned* active0, double* sol, int* status,")
             out.append("    unsigned* active, int max_iter) {")

@@ -111,28 +111,36 @@ class PseudoInverseController(BaseController):
         source, meta = emit_skill(pinv=prog, label=self.skill_spec.label)
         cubin, path = build.compile_cubin(source, tag="pinv_" + self.skill_spec.label)
         regs = build.kernel_registers(path, "clik_pinv_kernel")
-        if regs is not None and regs > 128 and "CLIK_MINBLOCKS" not in os.environ:
-            # Large skills (7-DOF pose tasks, many sets) are latency-bound at the 2-3 CTAs of 128 threads per
-            # SM their natural register allocation allows.  A register cap buys occupancy and costs spills;
-            # it wins while the spills stay small (measured, profiles/r2_ab.txt + r2_ab2.txt: iiwa pose skill
-            # 166 regs natural 1.20e10 steps/s, cap 128 regs / 200 B local 1.33e10, cap 96 regs / 360 B 1.08e10;
-            # before the chain pull-back shrank it: 208 regs natural 7.1e9, cap 168 / 368 B 7.7e9, cap 128 /
-            # 520 B 6.6e9; 9-row stress skill: 255 regs natural 4.6e9, cap 168 / 832 B 3.9e9).  Rule: the
-            # highest occupancy among 3 and 4 CTAs/SM whose local-memory frame stays within 400 B.
+        if regs is not None and "CLIK_MINBLOCKS" not in os.environ:
+            # Occupancy step by register cap (`__launch_bounds__(128, k)`).  These kernels are bound by the
+            # fp64 pipe and by dependency latency, so one more resident CTA per SM pays as long as the cap
+            # does not push live values into local memory.  Measured (profiles/r2_ab*.txt, 2^20 instances):
+            #   UR5 tracking   66 regs, 7 CTAs/SM 4.07e10 steps/s -> cap 8 (63 regs, no spill)      4.31e10
+            #   Moe-2016       92 regs, 5 CTAs    2.66e10         -> cap 7 (72 regs, +56 B local)    2.83e10
+            #   iiwa pose     166 regs, 3 CTAs    1.20e10         -> cap 4 (128 regs, 200 B local)   1.33e10,
+            #                                                        cap 5 (96 regs, 360 B)          1.08e10
+            #   iiwa stress   255 regs, 2 CTAs    4.6e9           -> cap 3 (168 regs, 832 B)         3.9e9
+            # Rule: take the highest occupancy step above the natural one whose local-memory frame stays
+            # within 64 B of the natural frame (small kernels) / within 400 B (kernels above 128 registers).
             natural = regs
-            for min_blocks, cap in ((4, 128), (3, 168)):
+            natural_local = build.kernel_stack_bytes(path, "clik_pinv_kernel") or 0
+            if natural > 128:
+                levels, limit = ((4, 128), (3, 168)), 400
+            else:
+                levels, limit = ((8, 64), (7, 72), (6, 80), (5, 96)), natural_local + 64
+            for min_blocks, cap in levels:
                 if natural <= cap:
                     continue
                 src_c, meta_c = emit_skill(pinv=prog, label=self.skill_spec.label, min_blocks=min_blocks)
                 cubin_c, path_c = build.compile_cubin(src_c, tag="pinv_" + self.skill_spec.label)
                 local_c = build.kernel_stack_bytes(path_c, "clik_pinv_kernel")
-                if local_c is not None and local_c <= 400:
+                if local_c is not None and local_c <= limit:
                     source, meta, cubin, path = src_c, meta_c, cubin_c, path_c
-                    meta["register_cap"] = ("launch_bounds(128, %d): natural allocation was %d registers, "
-                                            "%d B local memory under the cap" % (min_blocks, natural, local_c))
+                    meta["register_cap"] = ("launch_bounds(128, %d): natural allocation was %d registers / %d B "
+                                            "local, %d B local under the cap" % (min_blocks, natural, natural_local, local_c))
                     break
             else:
-                meta["register_cap"] = "none: natural allocation %d registers; a cap would spill more than 400 B" % natural
+                meta["register_cap"] = "none: natural allocation %d registers" % natural
         self.kernel_source, self.kernel_meta, self.cubin_path = source, meta, path
         self._nx, self._ny = prog.n_virt, prog.n_in
         self._cubin = cubin

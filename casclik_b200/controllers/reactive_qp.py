@@ -15,6 +15,8 @@ evaluates H, A, lb, ub and solves the QP per thread (csrc/clik_qp.cuh).  Infeasi
 not raise out of `solve_batch`; they are reported per instance in `status` (the single-instance
 `solve` raises RuntimeError like the reference's conic call does).
 """
+import os
+
 import numpy as np
 
 from .. import build, runtime
@@ -166,6 +168,20 @@ class ReactiveQPController(BaseController):
                              "(mu*robot weights; mu*virtual weights; mu + slack weights) are not" % bad)
         source, meta = emit_skill(qp=prog, label=self.skill_spec.label)
         cubin, path = build.compile_cubin(source, tag="qp_" + self.skill_spec.label)
+        regs = build.kernel_registers(path, "clik_qp_fast_kernel") if meta.get("qp_split") else None
+        if regs is not None and regs > 168 and "CLIK_QP_FAST_MINBLOCKS" not in os.environ:
+            # The fast kernel holds two phases: the prediction passes every instance runs, and the rarely
+            # executed continuation for slow instances (more passes + the one-row rule), whose register
+            # needs must not cost the first phase an occupancy step: cap at 3 CTAs/SM (168 registers) when
+            # the spills that causes stay small (UR5 9x15: 208 -> 168 registers; same rule as the pinv kernels).
+            src3, meta3 = emit_skill(qp=prog, label=self.skill_spec.label, qp_fast_min_blocks=3)
+            cubin3, path3 = build.compile_cubin(src3, tag="qp_" + self.skill_spec.label)
+            local3 = build.kernel_stack_bytes(path3, "clik_qp_fast_kernel")
+            natural_local = build.kernel_stack_bytes(path, "clik_qp_fast_kernel") or 0
+            if local3 is not None and local3 <= natural_local + 400:
+                source, meta, cubin, path = src3, meta3, cubin3, path3
+                meta["register_cap"] = ("fast kernel launch_bounds(128, 3): natural allocation was %d registers, "
+                                        "%d B local under the cap" % (regs, local3))
         self.kernel_source, self.kernel_meta, self.cubin_path = source, meta, path
         self._nxv, self._ny, self._qn, self._qm = prog.n_virt, prog.n_in, prog.nx, prog.m
         self.row_labels = prog.labels

@@ -32,6 +32,10 @@ enum : int { QP_OK = 0, QP_MAXITER = 1, QP_INFEASIBLE = 2, QP_PENDING = 3 /* tra
 
 // A solution containing NaN / inf is never reported as solved (a zero cost weight makes 1/sqrt(h) infinite,
 // a NaN input poisons every comparison of the iteration, which then "finds no violated row").
+// inf / NaN test on the high word (integer pipe): exponent field all ones
+__device__ __forceinline__ bool finite_bits(double v) {
+  return (__double2hiint(v) & 0x7ff00000) != 0x7ff00000;
+}
 template <int N> __device__ __forceinline__ bool all_finite(const double (&x)[N]) {
   bool ok = true;
 #pragma unroll
@@ -614,9 +618,21 @@ __device__ __forceinline__ void masks_from_x0(const QpSData<S>& D, const double 
 // (at most CRASH_PASSES; UR5 problem: 0.04 % of the instances are not final after 8 passes, 0.005 % after 12).  qp_structured then starts from the guess, repairs whatever is left and
 // certifies the result, so the answer never depends on it.
 constexpr int CRASH_PASSES = 12;
-template <class S>
+// MAXP: pass budget.  The fast pass of the two-launch form stops early (S::QP_FAST_PASSES): a warp runs
+// until its SLOWEST lane is final, so with 32 instances per warp the average warp of the UR5 problem ran
+// 6.2 passes although 83 % of the instances are final after 3 — the few slow ones are cheaper in the tail
+// pass, which packs them densely and continues the passes from the parked set.
+// SINGLE: apply only ONE of the changes a pass proposes (the most violated row if the face optimum is
+// infeasible, else the held row with the worst multiplier).  The all-at-once passes can cycle between two
+// sets (0.005 % of the UR5 instances never settle); changing one row at a time is the classical primal-dual
+// pivoting rule and settles them, at one row per pass.  Used after the all-at-once budget is spent, in the
+// kernels that hold the full solver anyway (never in the fast pass), so that almost nothing is left for
+// the Goldfarb-Idnani iteration, whose single-thread latency (~30 us with its spills) was the whole
+// duration of the tail launch.
+constexpr int CRASH_SINGLE_PASSES = 30;
+template <class S, int MAXP = CRASH_PASSES, bool SINGLE = false>
 __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*in: guess, out*/,
-                                            unsigned* lo, double (&xout)[S::QN]) {
+                                            unsigned* lo, double (&xout)[S::QN], bool* still_changing = nullptr) {
   constexpr int NX = S::QN, MD = S::QMD, MU = S::QMU, MD1 = MD > 0 ? MD : 1;
   bool eq[MD1];
   double s2[NX], yv[MD1];
@@ -647,7 +663,7 @@ __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*
   }
   bool certified = false;            // this thread's set stopped changing and its face optimum passes the KKT check
 #pragma unroll 1
-  for (int pass = 0; pass < CRASH_PASSES; ++pass) {
+  for (int pass = 0; pass < MAXP; ++pass) {
     double xf[NX], w[NX];            // value of a fixed variable (0 if free); 1/h_j of a free one (0 if fixed)
 #pragma unroll
     for (int j = 0; j < NX; ++j) xf[j] = 0.0;
@@ -742,11 +758,12 @@ __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*
     }
     bool changed = false;
 #pragma unroll
-    for (int j = 0; j < NX; ++j) { changed = changed || (nf[j] != fr[j]); fr[j] = nf[j]; }
+    for (int j = 0; j < NX; ++j) changed = changed || (nf[j] != fr[j]);
     // dense inequality rows: keep while the multiplier (-y for upper, +y for lower) is non-negative,
     // take up when the face optimum violates them (equality rows always stay)
-#pragma unroll
     bool held_ok = true;             // every held dense row really sits on its bound (the Gram solve was accurate)
+    int nd[MD1];
+    double dviol[MD1];
 #pragma unroll
     for (int a = 0; a < MD; ++a) {
       double r = 0.0;
@@ -761,11 +778,46 @@ __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*
       }
       na = eq[a] ? 1 : na;
       changed = changed || (na != da[a]);
-      da[a] = na;
+      nd[a] = na;
+      dviol[a] = fmax(r - D.ubd[a], D.lbd[a] - r);
+    }
+    if constexpr (SINGLE) {
+      double best = 0.0;
+      int pick = -1;                   // 0..NX-1: variable, NX..: dense row
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        if (nf[j] != fr[j] && viol[j] > best) { best = viol[j]; pick = j; }
+      }
+#pragma unroll
+      for (int a = 0; a < MD; ++a) {
+        if (nd[a] != da[a] && da[a] == 0 && dviol[a] > best) { best = dviol[a]; pick = NX + a; }
+      }
+      if (pick < 0) {                  // primal feasible: release the worst multiplier
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+          if (nf[j] != fr[j] && fabs(gs[j]) >= best) { best = fabs(gs[j]); pick = j; }
+        }
+#pragma unroll
+        for (int a = 0; a < MD; ++a) {
+          if (nd[a] != da[a] && fabs(yv[a]) >= best) { best = fabs(yv[a]); pick = NX + a; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NX; ++j) fr[j] = (pick == j) ? nf[j] : fr[j];
+#pragma unroll
+      for (int a = 0; a < MD; ++a) da[a] = (pick == NX + a) ? nd[a] : da[a];
+    } else {
+#pragma unroll
+      for (int j = 0; j < NX; ++j) fr[j] = nf[j];
+#pragma unroll
+      for (int a = 0; a < MD; ++a) da[a] = nd[a];
     }
     // unchanged set = every row feasible, every multiplier of the right sign: the face optimum is the
     // minimiser.  (A later pass of a thread that waits for its warp recomputes the same numbers.)
     certified = !changed && held_ok;
+    // (a set that stopped changing without certifying — an inaccurate Gram solve near a singular task
+    // Jacobian — will not be helped by more passes: the caller goes straight to the iteration)
+    if (still_changing != nullptr) *still_changing = changed;
 #pragma unroll
     for (int j = 0; j < NX; ++j) xout[j] = xc[j];
     if (!__any_sync(__activemask(), changed)) break;
@@ -799,10 +851,16 @@ template <class S> struct QpData {
 };
 
 // One instance of the fused step: load, evaluate the skill's QP matrices, solve, store.
-// MODE QP_FAST: only the working-set prediction runs; an instance it cannot certify is marked
-// QP_PENDING in status[i], its uncertified prediction is parked in active[] (if present), nothing else
-// is written.  MODE QP_TAIL: the full solver for such an instance, started from the parked prediction.
+// MODE QP_FAST: the first S::QP_FAST_PASSES prediction passes; an instance they cannot certify is marked
+// QP_PENDING in status[i], its uncertified set is parked in active[] (if present), nothing else is written.
+// MODE QP_TAIL: such an instance, packed densely with the other slow ones: the rest of the all-at-once
+// budget and the one-row passes from the parked set, then the Goldfarb-Idnani iteration for what is still
+// uncertified (the whole path when there is no active[] to park in).  MODE QP_FULL: everything, one thread.
+// FAST -> TAIL run exactly the pass sequence of FULL, hence the same bits.
 enum : int { QP_FULL = 0, QP_FAST = 1, QP_TAIL = 2 };
+#ifdef CLIK_QP_STATS
+static long long qp_stats[8];   // host-harness instrumentation: [0] instances entering Goldfarb-Idnani, [1] one-row phases
+#endif
 template <class S, int MODE>
 __device__ __forceinline__ void qp_instance(long long ld, long long i, const double* __restrict__ t, int t_stride,
                                             const double* __restrict__ q, const double* __restrict__ x,
@@ -811,14 +869,15 @@ __device__ __forceinline__ void qp_instance(long long ld, long long i, const dou
                                             int* __restrict__ status, unsigned* active, int max_iter) {
   double qv[S::NQ > 0 ? S::NQ : 1], xv[S::NX > 0 ? S::NX : 1], yv[S::NY > 0 ? S::NY : 1];
   const double tv = __ldcs(t + (long long)t_stride * i);
+  bool data_ok = finite_bits(tv);
 #pragma unroll
-  for (int j = 0; j < S::NQ; ++j) qv[j] = __ldcs(q + (long long)j * ld + i);
+  for (int j = 0; j < S::NQ; ++j) { qv[j] = __ldcs(q + (long long)j * ld + i); data_ok = data_ok && finite_bits(qv[j]); }
 #pragma unroll
-  for (int j = 0; j < S::NX; ++j) xv[j] = __ldcs(x + (long long)j * ld + i);
+  for (int j = 0; j < S::NX; ++j) { xv[j] = __ldcs(x + (long long)j * ld + i); data_ok = data_ok && finite_bits(xv[j]); }
 #pragma unroll
-  for (int j = 0; j < S::NY; ++j) yv[j] = __ldcs(y + (long long)j * ld + i);
+  for (int j = 0; j < S::NY; ++j) { yv[j] = __ldcs(y + (long long)j * ld + i); data_ok = data_ok && finite_bits(yv[j]); }
   double xs[S::QN];
-  unsigned mu, ml;
+  unsigned mu = 0u, ml = 0u;
   int st;
   if constexpr (S::QSTRUCT) {
     QpSData<S> d;
@@ -847,13 +906,28 @@ __device__ __forceinline__ void qp_instance(long long ld, long long i, const dou
     }
     // predicts the working set from any guess, or none; when the prediction certifies itself its
     // face optimum is the answer and the iteration below is skipped
-    bool solved = false;
-    if (S::QP_CRASH && !parked) solved = crash_guess<S>(d, &wu, &wl, xs) && S::QP_CRASH_FINAL && all_finite(xs);
+    constexpr int REST = CRASH_PASSES - S::QP_FAST_PASSES > 1 ? CRASH_PASSES - S::QP_FAST_PASSES : 1;
+    bool ok = false;
+    if constexpr (MODE == QP_FAST) {
+      if (S::QP_CRASH) ok = crash_guess<S, S::QP_FAST_PASSES>(d, &wu, &wl, xs);
+    } else {
+      if (S::QP_CRASH) {
+        bool cycling = false;
+        ok = parked ? crash_guess<S, REST>(d, &wu, &wl, xs, &cycling) : crash_guess<S>(d, &wu, &wl, xs, &cycling);
+        if (!ok && cycling && S::QP_CRASH_SINGLE) {
+#ifdef CLIK_QP_STATS
+          ++qp_stats[1];
+#endif
+          ok = crash_guess<S, CRASH_SINGLE_PASSES, true>(d, &wu, &wl, xs);
+        }
+      }
+    }
+    const bool solved = ok && S::QP_CRASH_FINAL && all_finite(xs) && data_ok;
     st = solved ? QP_OK : QP_MAXITER;
     mu = wu;
     ml = wl;
     if constexpr (MODE == QP_FAST) {
-      if (!solved) {
+      if (!solved && data_ok) {
         status[i] = QP_PENDING;
         if (active != nullptr) {
           active[i] = wu;
@@ -862,8 +936,11 @@ __device__ __forceinline__ void qp_instance(long long ld, long long i, const dou
         return;
       }
     } else {
+#ifdef CLIK_QP_STATS
+      if (!solved && data_ok) ++qp_stats[0];
+#endif
 #pragma unroll 1
-      for (int attempt = 0; attempt < 2 && !solved; ++attempt) {   // a bad guess must never cost the answer:
+      for (int attempt = 0; attempt < 2 && !solved && data_ok; ++attempt) {   // a bad guess must never cost the answer:
         if (attempt > 0) {                                         // second attempt = cold start
           wu = wl = 0u;
           S::eval_qps(tv, qv, xv, yv, d);
@@ -878,7 +955,12 @@ __device__ __forceinline__ void qp_instance(long long ld, long long i, const dou
     st = qp_dual_active_set<S::QN, S::QM>(S::QN, S::QM, d.A, d.lb, d.ub, d.h, nullptr, xs, &mu, &ml,
                                           max_iter);
   }
-  if (st == QP_OK && !all_finite(xs)) st = QP_INVALID;
+  // NaN / inf in the inputs or in the solution is never "solved": the iteration sees every comparison
+  // with a NaN as false and would report the start point as optimal
+  if (!data_ok || !all_finite(xs)) {
+    st = QP_INVALID;
+    mu = ml = 0u;
+  }
   for (int j = 0; j < S::QN; ++j) __stcs(sol + (long long)j * ld + i, xs[j]);
   if (status != nullptr) status[i] = st;
   if (active != nullptr) {
@@ -961,7 +1043,12 @@ __device__ __forceinline__ void qp_rollout(long long N, long long ld, int steps,
         S::eval_qps(tv, qv, xv, yv, d);
         unsigned wu = mu, wl = ml;
         bool solved = false;            // previous step's set -> this step's (usually one pass)
-        if (S::QP_CRASH) solved = crash_guess<S>(d, &wu, &wl, xs) && S::QP_CRASH_FINAL && all_finite(xs);
+        if (S::QP_CRASH) {
+          bool cycling = false;
+          bool ok = crash_guess<S>(d, &wu, &wl, xs, &cycling);
+          if (!ok && cycling && S::QP_CRASH_SINGLE) ok = crash_guess<S, CRASH_SINGLE_PASSES, true>(d, &wu, &wl, xs);
+          solved = ok && S::QP_CRASH_FINAL && all_finite(xs);
+        }
         st = solved ? QP_OK : QP_MAXITER;
         if (solved) { mu = wu; ml = wl; }
 #pragma unroll 1
@@ -979,7 +1066,7 @@ __device__ __forceinline__ void qp_rollout(long long N, long long ld, int steps,
         st = qp_dual_active_set<S::QN, S::QM>(S::QN, S::QM, d.A, d.lb, d.ub, d.h, nullptr, xs, &mu, &ml,
                                               max_iter);
       }
-      if (st == QP_OK && !all_finite(xs)) st = QP_INVALID;
+      if (!all_finite(xs)) st = QP_INVALID;   // whatever the iteration made of NaN / inf data
       if (st != QP_OK) {
         ++failed;
         for (int j = 0; j < S::QN; ++j) xs[j] = 0.0;

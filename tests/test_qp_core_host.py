@@ -15,6 +15,7 @@ from oracle_bridge import orc
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHIM = r'''
 #include <cmath>
+#include <cstring>
 #define __device__
 #define __forceinline__ inline
 #define __restrict__
@@ -27,6 +28,7 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline unsigned __activemask() { return 1u; }
 static inline int __any_sync(unsigned, int p) { return p; }
+static inline int __double2hiint(double x) { long long b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
 using std::fma; using std::fmax; using std::fmin; using std::fabs; using std::sqrt;
 #include "%s"
 extern "C" int host_qp(int nx, int m, double* A, const double* lb, const double* ub, const double* h,
@@ -162,6 +164,22 @@ extern "C" int host_crash(const double* Ad, const double* lbd, const double* ubd
   for (int j = 0; j < S::QN; ++j) x[j] = xs[j];
   return certified ? 1 : 0;
 }
+extern "C" int host_crash_single(const double* Ad, const double* lbd, const double* ubd, const double* lbu,
+                                 const double* ubu, const double* s, unsigned* wu /*in/out*/, unsigned* wl, double* x) {
+  // what the non-fast kernels do after the all-at-once budget: one-row-per-pass passes from the last set
+  clik::QpSData<S> d;
+  std::memcpy(d.Ad, Ad, sizeof(d.Ad)); std::memcpy(d.lbd, lbd, sizeof(d.lbd)); std::memcpy(d.ubd, ubd, sizeof(d.ubd));
+  std::memcpy(d.lbu, lbu, sizeof(d.lbu)); std::memcpy(d.ubu, ubu, sizeof(d.ubu)); std::memcpy(d.s, s, sizeof(d.s));
+  double xs[S::QN];
+  bool certified = clik::crash_guess<S>(d, wu, wl, xs);
+  int stage = certified ? 1 : 0;
+  if (!certified) {
+    certified = clik::crash_guess<S, clik::CRASH_SINGLE_PASSES, true>(d, wu, wl, xs);
+    stage = certified ? 2 : 0;
+  }
+  for (int j = 0; j < S::QN; ++j) x[j] = xs[j];
+  return stage;
+}
 extern "C" int host_qps(const double* Ad, const double* lbd, const double* ubd, const double* lbu,
                         const double* ubu, const double* s, double* x, unsigned* au, unsigned* al, int max_iter,
                         unsigned wu, unsigned wl) {
@@ -210,6 +228,17 @@ def host_qps(tmp_path_factory):
         crash.x = x
         return wu.value, wl.value
     solve.crash = crash
+
+    def crash_single(h, A, lb, ub):
+        ur = [r for r, _, _ in UNIT]
+        arrs = [A[DENSE_ROWS], lb[DENSE_ROWS], ub[DENSE_ROWS], lb[ur], ub[ur], 1.0 / np.sqrt(h)]
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
+        wu, wl = ctypes.c_uint(0), ctypes.c_uint(0)
+        x = np.zeros(6)
+        stage = lib.host_crash_single(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs], ctypes.byref(wu),
+                                      ctypes.byref(wl), x.ctypes.data_as(ctypes.c_void_p))
+        return stage, x, wu.value, wl.value
+    solve.crash_single = crash_single
     return solve
 
 
@@ -298,6 +327,30 @@ def test_structured_solver_warm_start_never_changes_the_answer(host_qps):
             assert kk["primal"] < 1e-9 and kk["stationarity"] < 1e-9 and kk["sign"] < 1e-9, (trial, g, kk)
             assert (auw, alw) == (au, al), (trial, g)
     assert n_warm_ok > 1000
+
+
+def test_single_change_passes_settle_what_the_all_at_once_passes_leave_and_certify_only_minimisers(host_qps):
+    """crash_guess<.., SINGLE>: after the all-at-once budget, one row changes per pass.  Whatever it certifies
+    is the minimiser with the solver's working set; it leaves (almost) nothing for the iteration."""
+    rng = np.random.default_rng(71)
+    stages = {0: 0, 1: 0, 2: 0}
+    n_feasible = 0
+    for trial in range(600):
+        h, A, lb, ub = _structured_problem(rng, eq_prob=3.0 if trial % 2 else 0.3, tight=(trial % 3 == 0))
+        x, st, au, al = host_qps(h, A, lb, ub)
+        stage, xc, wu, wl = host_qps.crash_single(h, A, lb, ub)
+        if st == 0:
+            n_feasible += 1
+            stages[stage] += 1
+        if stage:
+            assert st == 0 and (wu, wl) == (au, al), trial
+            assert np.abs(xc - x).max() < 1e-9 * (1 + np.abs(x).max()), trial
+            kk = orc.kkt_residuals(h, A, lb, ub, xc)
+            assert kk["primal"] < 1e-9 and kk["stationarity"] < 1e-9 and kk["sign"] < 1e-9, (trial, kk)
+    assert stages[2] > 0                                   # the single-change passes did rescue some
+    # (what is left on these deliberately nasty problems — dependent rows, two rows of one column active,
+    # contradictory bounds — is the Goldfarb-Idnani iteration's job)
+    assert stages[0] <= 0.1 * n_feasible, stages
 
 
 def test_crash_start_guess_is_sound_and_never_changes_the_answer(host_qps):
