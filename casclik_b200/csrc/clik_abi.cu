@@ -181,7 +181,7 @@ __global__ void clik_qp_dense_kernel(long long N, int nx, int m, const double* _
     int st = clik::qp_dual_active_set<NXC, MC>(nx, m, Al, lbl, ubl, hl, x0 ? x0l : nullptr, xs, &mu, &ml, max_iter);
     bool finite = true;
     for (int j = 0; j < nx; ++j) finite = finite && (fabs(xs[j]) < INFINITY);
-    if (!finite) st = clik::QP_INVALID;
+    if (st == clik::QP_OK && !finite) st = clik::QP_INVALID;
     for (int j = 0; j < nx; ++j) sol[(long long)j * N + i] = xs[j];
     if (status) status[i] = st;
     if (active) { active[i] = mu; active[N + i] = ml; }

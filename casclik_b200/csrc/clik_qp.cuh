@@ -957,7 +957,7 @@ __device__ __forceinline__ void qp_instance(long long ld, long long i, const dou
   }
   // NaN / inf in the inputs or in the solution is never "solved": the iteration sees every comparison
   // with a NaN as false and would report the start point as optimal
-  if (!data_ok || !all_finite(xs)) {
+  if (!data_ok || (st == QP_OK && !all_finite(xs))) {
     st = QP_INVALID;
     mu = ml = 0u;
   }
@@ -1066,7 +1066,7 @@ __device__ __forceinline__ void qp_rollout(long long N, long long ld, int steps,
         st = qp_dual_active_set<S::QN, S::QM>(S::QN, S::QM, d.A, d.lb, d.ub, d.h, nullptr, xs, &mu, &ml,
                                               max_iter);
       }
-      if (!all_finite(xs)) st = QP_INVALID;   // whatever the iteration made of NaN / inf data
+      if (st == QP_OK && !all_finite(xs)) st = QP_INVALID;
       if (st != QP_OK) {
         ++failed;
         for (int j = 0; j < S::QN; ++j) xs[j] = 0.0;

@@ -43,7 +43,7 @@ def test_argument_validation_needs_no_device():
     assert b"NULL" in lib.clik_last_error()
     assert lib.clik_pinv_step(None, 4, None, 0, None, None, None, None, None, None, None) == 1
     assert lib.clik_qp_dense(0, 4, 99, 3, None, None, None, None, None, None, None, None, 0, None) == 1
-    assert b"nx <= 16" in lib.clik_last_error()
+    assert b"nx <= 32, m <= 64" in lib.clik_last_error()
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -15,6 +15,8 @@ if [ "${FULL:-1}" = "1" ]; then
       python bench.py --secondary-only iiwa_multitask > /dev/null 2> gpurun_out/r2_prof_iiwa.err
   ncu --set full --clock-control none --import-source on -k regex:clik_qp_tail_kernel -s 4 -c 1 -f -o gpurun_out/r2_prof_qp_tail \
       python bench.py --secondary-only ur5_qp > /dev/null 2> gpurun_out/r2_prof_qp_tail.err
+  ncu --set full --clock-control none --import-source on -k regex:clik_qp_fast_kernel -s 4 -c 1 -f -o gpurun_out/r2_prof_qp_fast \
+      python bench.py --secondary-only ur5_qp > /dev/null 2> gpurun_out/r2_prof_qp_fast.err
   ncu --set full --clock-control none --import-source on -k regex:clik_pinv_kernel -s 6 -c 1 -f -o gpurun_out/r2_prof_ur5_track \
       python bench.py --no-secondary --no-cpu-baseline --steps 6 --warmup 3 --e2e-steps 1 > /dev/null 2> gpurun_out/r2_prof_ur5_track.err
 fi
