@@ -548,6 +548,10 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out.append("  }")
         meta["qp_eval"] = em.counts()
         meta["qp_read_masks"] = em.read_masks(qp.syms)
+        # rows the program reads: only those are fetched and checked for NaN / inf (the host entry
+        # points upload only those, the others are undefined in the device copy)
+        out.append("  static constexpr unsigned QP_READ_T = %du, QP_READ_Q = 0x%xu, QP_READ_X = 0x%xu, QP_READ_Y = 0x%xu;"
+                   % meta["qp_read_masks"])
         meta["qp_inputs_read"] = em.inputs_read()
         meta["qp_bytes_per_step"] = 8 * em.inputs_read() + 8 * qp.nx + 4 + 8
 

@@ -36,6 +36,7 @@ enum : int { QP_OK = 0, QP_MAXITER = 1, QP_INFEASIBLE = 2, QP_PENDING = 3 /* tra
 __device__ __forceinline__ bool finite_bits(double v) {
   return (__double2hiint(v) & 0x7ff00000) != 0x7ff00000;
 }
+__device__ __forceinline__ constexpr bool row_read(unsigned mask, int j) { return j >= 32 || ((mask >> j) & 1u) != 0u; }
 template <int N> __device__ __forceinline__ bool all_finite(const double (&x)[N]) {
   bool ok = true;
 #pragma unroll
@@ -868,14 +869,25 @@ __device__ __forceinline__ void qp_instance(long long ld, long long i, const dou
                                             const unsigned* active0, double* __restrict__ sol,
                                             int* __restrict__ status, unsigned* active, int max_iter) {
   double qv[S::NQ > 0 ? S::NQ : 1], xv[S::NX > 0 ? S::NX : 1], yv[S::NY > 0 ? S::NY : 1];
-  const double tv = __ldcs(t + (long long)t_stride * i);
+  // only the rows the generated program reads are fetched and tested (S::QP_READ_*): an unread row may
+  // be anything — the host entry points do not even upload it
+  const double tv = S::QP_READ_T ? __ldcs(t + (long long)t_stride * i) : 0.0;
   bool data_ok = finite_bits(tv);
 #pragma unroll
-  for (int j = 0; j < S::NQ; ++j) { qv[j] = __ldcs(q + (long long)j * ld + i); data_ok = data_ok && finite_bits(qv[j]); }
+  for (int j = 0; j < S::NQ; ++j) {
+    qv[j] = row_read(S::QP_READ_Q, j) ? __ldcs(q + (long long)j * ld + i) : 0.0;
+    data_ok = data_ok && finite_bits(qv[j]);
+  }
 #pragma unroll
-  for (int j = 0; j < S::NX; ++j) { xv[j] = __ldcs(x + (long long)j * ld + i); data_ok = data_ok && finite_bits(xv[j]); }
+  for (int j = 0; j < S::NX; ++j) {
+    xv[j] = row_read(S::QP_READ_X, j) ? __ldcs(x + (long long)j * ld + i) : 0.0;
+    data_ok = data_ok && finite_bits(xv[j]);
+  }
 #pragma unroll
-  for (int j = 0; j < S::NY; ++j) { yv[j] = __ldcs(y + (long long)j * ld + i); data_ok = data_ok && finite_bits(yv[j]); }
+  for (int j = 0; j < S::NY; ++j) {
+    yv[j] = row_read(S::QP_READ_Y, j) ? __ldcs(y + (long long)j * ld + i) : 0.0;
+    data_ok = data_ok && finite_bits(yv[j]);
+  }
   double xs[S::QN];
   unsigned mu = 0u, ml = 0u;
   int st;

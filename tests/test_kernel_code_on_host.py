@@ -380,3 +380,35 @@ def test_fuzzed_option_skills_kernel_source_on_host_vs_oracle(seed, tmp_path):
     assert np.array_equal(mode, ref_mode) and len(np.unique(ref_mode)) >= 2
     err = np.linalg.norm(qdot - ref_v, axis=0) / np.maximum(np.linalg.norm(ref_v, axis=0), 1e-12)
     assert err.max() < 1e-6, err.max()
+
+
+def test_qp_kernel_ignores_input_rows_the_program_does_not_read(tmp_path):
+    """The host entry points upload only the rows the compiled program reads (clik_abi.cu rowmask), so
+    whatever sits in the other rows of the device copy must influence neither the solution nor the
+    NaN / inf screening of the inputs (status 4)."""
+    from casclik_b200 import scenarios
+    sc = scenarios.get("ur5_qp")
+    ctrl = sc.make_controller()
+    lib = _host_library(ctrl, tmp_path)
+    tmask, qmask, _, _ = ctrl.kernel_meta["qp_read_masks"]
+    assert tmask == 0 and qmask == 63, "this tracking QP reads every joint and not the time"
+    N = 64
+    inp = {k: v for k, v in sc.sample(N, seed=0).items() if v is not None}
+    t, q, x, y = _inputs(inp)
+    res = []
+    for poison in (False, True):
+        qq, tt = q.copy(), t.copy()
+        if poison:
+            tt[:] = np.nan
+        sol, status = np.full((9, N), np.nan), np.full(N, -9, dtype=np.int32)
+        active = np.zeros((2, N), dtype=np.uint32)
+        lib.clik_qp_kernel(ctypes.c_longlong(N), ctypes.c_longlong(N), _p(tt), ctypes.c_int(1), _p(qq), _p(x), _p(y), None,
+                           None, _p(sol), _p(status), _p(active), ctypes.c_int(240))
+        assert np.all(status == 0)
+        res.append(sol)
+    assert np.array_equal(res[0], res[1])
+    qq = q.copy()
+    qq[0, 3] = np.inf                                  # a row that IS read: screened
+    lib.clik_qp_kernel(ctypes.c_longlong(N), ctypes.c_longlong(N), _p(t), ctypes.c_int(1), _p(qq), _p(x), _p(y), None,
+                       None, _p(sol), _p(status), _p(active), ctypes.c_int(240))
+    assert status[3] == 4 and np.all(np.delete(status, 3) == 0)
