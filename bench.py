@@ -231,13 +231,22 @@ def _launches_per_step(meta, is_qp):
     return 2 if (meta.get("pinv_split") and os.environ.get("CLIK_PINV_SPLIT", "1") != "0") else 1
 
 
+def _overlap_note(level):
+    return {0: "0: plain stream order",
+            1: "1: plain stream order between steps (the two launches of a two-launch step overlap)",
+            2: "2: the K steps are independent batches on disjoint buffers; a step kernel may start while the "
+               "previous one drains (programmatic dependent launch), completion stays in stream order; "
+               "`stream_ordered` is the same loop without it"}[level]
+
+
 def _bytes_per_set(meta, is_qp, B):
     return (meta["qp_bytes_per_step"] if is_qp else meta["pinv_bytes_per_step"]) * B
 
 
 def time_device_resident(torch, dist, ctrl, scenario, B, steps, warm, rank, world, dev, min_sets=2,
-                         seed_base=1000):
-    """K steps of solve_batch on device-resident inputs -> (ms total max-over-ranks, n_sets, graph?, step).
+                         seed_base=1000, overlap=2, plain_too=True):
+    """K steps of solve_batch on device-resident inputs -> (ms total max-over-ranks, n_sets, graph?, step,
+    ms of the same K steps in plain stream order | None).
     Inputs and outputs rotate over enough sets to exceed L2 twice over."""
     meta = ctrl.kernel_meta
     is_qp = scenario.controller == "qp"
@@ -267,40 +276,52 @@ def time_device_resident(torch, dist, ctrl, scenario, B, steps, warm, rank, worl
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(warm, 3)):
-        step(i)
-    barrier()
-    # The K timed steps are K launches of the step kernel through the C ABI.  They are captured once
-    # into a CUDA graph and replayed, so that host jitter (8 ranks sharing the box's cores with the
-    # clock samplers) cannot turn a 27 us kernel into a launch-bound loop; same kernels, same inputs.
-    graph = None
-    if os.environ.get("CLIK_BENCH_GRAPH", "1") == "1":
-        try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for i in range(steps):
-                    step(i)
-            g.replay()                       # untimed: uploads the graph
-            graph = g
-        except Exception as exc:             # capture not possible: time the plain launch loop
-            sys.stderr.write("bench: CUDA graph capture failed (%s); timing direct launches\n" % exc)
-            graph = None
-        torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    if graph is not None:
-        graph.replay()
-    else:
-        for i in range(steps):
+    def timed(level):
+        """K timed steps at overlap level `level` -> (ms max-over-ranks, replayed from a graph?)."""
+        ctrl.set_overlap(level)
+        for i in range(max(warm, 3)):
             step(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    return float(tms.item()), n_sets, graph is not None, step
+        barrier()
+        # The K timed steps are K launches of the step kernel through the C ABI.  They are captured once
+        # into a CUDA graph and replayed, so that host jitter (8 ranks sharing the box's cores with the
+        # clock samplers) cannot turn a 27 us kernel into a launch-bound loop; same kernels, same inputs.
+        graph = None
+        if os.environ.get("CLIK_BENCH_GRAPH", "1") == "1":
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for i in range(steps):
+                        step(i)
+                g.replay()                       # untimed: uploads the graph
+                graph = g
+            except Exception as exc:             # capture not possible: time the plain launch loop
+                sys.stderr.write("bench: CUDA graph capture failed (%s); timing direct launches\n" % exc)
+                graph = None
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        if graph is not None:
+            graph.replay()
+        else:
+            for i in range(steps):
+                step(i)
+        e1.record()
+        barrier()
+        tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        return float(tms.item()), graph is not None
+
+    # The K steps are K independent batches (disjoint rotating buffers), so the stream may overlap the
+    # tail of one step kernel with the ramp of the next (programmatic dependent launch, overlap level 2:
+    # include/clik.h clik_skill_set_overlap; kernels still complete in stream order).  The same K steps in
+    # plain stream order (level 1) are timed as well and reported next to the value.
+    ms_plain = None
+    if overlap >= 2 and plain_too:
+        ms_plain, _ = timed(1)
+    ms, graphed = timed(overlap)
+    return ms, n_sets, graphed, step, ms_plain
 
 
 def rooflines(meta, is_qp, B, sec_per_step, hbm_peak, hbm_src, fp64_peak, counts):
@@ -351,6 +372,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 20, help="instances per GPU per step")
     ap.add_argument("--sets", type=int, default=0, help="resident input/output sets rotated over (0 = enough for 300 MB)")
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--overlap", type=int, default=int(os.environ.get("CLIK_PDL", "2")), choices=[0, 1, 2],
+                    help="clik_skill_set_overlap level of the device-resident loop (2: independent steps overlap)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs")
     ap.add_argument("--secondary-only", default="", help="(profiling) run only this secondary scenario's timed loop")
@@ -405,14 +428,16 @@ def main():
             Bs = batch
         per = _bytes_per_set(c.kernel_meta, qp, Bs)
         k = int(max(8, min(100, (3 << 30) // max(per, 1))))          # ~3 GB of algorithmic traffic per leg
-        ms_tot, n_sets, graphed, _ = time_device_resident(torch, dist, c, sc, Bs, k, 3, rank, world, dev,
-                                                          seed_base=2000)
+        ms_tot, n_sets, graphed, _, ms_plain = time_device_resident(torch, dist, c, sc, Bs, k, 3, rank, world, dev,
+                                                                    seed_base=2000, overlap=args.overlap)
         total = batch if mode == "strong" else batch * world
         val = total * k / (ms_tot * 1e-3)
         out = {"config": cfg, "workload": sc.description, "value": val, "unit": UNIT,
                "ms_per_step": ms_tot / k, "steps": k, "batch_per_gpu": Bs, "global_batch": total,
-               "scaling": mode, "sets_rotated": n_sets,
+               "scaling": mode, "sets_rotated": n_sets, "overlap": _overlap_note(args.overlap),
                "gpu_launches": k * _launches_per_step(c.kernel_meta, qp)}
+        if ms_plain is not None:
+            out["stream_ordered"] = {"value": total * k / (ms_plain * 1e-3), "ms_per_step": ms_plain / k}
         if rank == 0:
             roof, detail = rooflines(c.kernel_meta, qp, Bs, ms_tot * 1e-3 / k, hbm_peak, hbm_src, fp64_peak,
                                      counts_all.get(name, {}))
@@ -438,8 +463,9 @@ def main():
     # on the data path — instances are independent
     sampler = ClockSampler(local)
     sampler.start()
-    ms, n_sets, graphed, step = time_device_resident(torch, dist, ctrl, scenario, B, args.steps, args.warmup,
-                                                     rank, world, dev, min_sets=max(args.sets, 2))
+    ms, n_sets, graphed, step, ms_plain = time_device_resident(torch, dist, ctrl, scenario, B, args.steps, args.warmup,
+                                                               rank, world, dev, min_sets=max(args.sets, 2),
+                                                               overlap=args.overlap)
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- end to end through the host-buffer C ABI (pinned host inputs, copies inside) --------------
@@ -508,6 +534,7 @@ def main():
                        "parallelism": "independent shards, one per GPU, no collective on the data path",
                        "launch_mode": ("%d step-kernel launches replayed from one CUDA graph" % args.steps
                                        if graphed else "direct launches"),
+                       "overlap": _overlap_note(args.overlap),
                        "host_affinity": ("rank 0 bound to its GPU's NUMA node: %d of %d CPUs" % (len(numa[1]), len(numa[0]))
                                          if numa else "unbound"),
                        "l2": "rotating %d resident input + output sets (%d MB of algorithmic traffic in total) "
@@ -524,6 +551,10 @@ def main():
             "gpu_launches": args.steps * _launches_per_step(meta, is_qp),
             "clocks": clocks,
         }
+        if ms_plain is not None:
+            # the same K steps with every step kernel waiting for the previous one to finish (overlap level 1)
+            line["stream_ordered"] = {"value": world * B * args.steps / (ms_plain * 1e-3), "unit": UNIT,
+                                      "ms_per_step": ms_plain / args.steps}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"], _, _ = CpuPort(scenario).measure(B, seconds_target=12.0)
     del step

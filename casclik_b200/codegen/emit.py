@@ -570,7 +570,9 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         meta["pinv_unroll"] = unroll
         pf = int(os.environ.get("CLIK_PREFETCH_CTAS", "0"))
         meta["pinv_prefetch_ctas"] = pf
+        out.append("  clik::pdl_launch_dependents();")
         out.append("  clik::pinv_step<Skill, %d, %d>(N, ld, t, t_stride, q, x, y, qdot, xdot, mode);" % (unroll, pf))
+        out.append("  clik::pdl_wait();")
         out.append("}")
         # (the rollout kernel keeps its state across steps in registers: the step kernel's occupancy cap,
         # chosen from the step kernel's spill size, does not transfer to it)
@@ -586,13 +588,17 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
             out.append('extern "C" __global__ void %s clik_pinv_fast_kernel(' % bounds)
             out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
             out.append("    const double* y, double* qdot, double* xdot, int* mode) {")
+            out.append("  clik::pdl_launch_dependents();")
             out.append("  clik::pinv_step<Skill, %d, %d, true>(N, ld, t, t_stride, q, x, y, qdot, xdot, mode);" % (unroll, pf))
+            out.append("  clik::pdl_wait();")
             out.append("}")
         if meta.get("pinv_group"):
             # sub-warp mapping (clik_pinv_group.cuh): tail of the fast pass, or whole batches on request
             out.append('extern "C" __global__ void __launch_bounds__(clik::GroupGeometry<Skill>::BLOCK) clik_pinv_group_kernel(')
             out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
             out.append("    const double* y, double* qdot, double* xdot, int* mode, int from_mode, int only_pending) {")
+            out.append("  clik::pdl_launch_dependents();")
+            out.append("  clik::pdl_wait();   // reads the mode[] the fast pass wrote")
             out.append("  clik::pinv_group_step<Skill>(N, ld, t, t_stride, q, x, y, qdot, xdot, mode, from_mode, only_pending);")
             out.append("}")
         if os.environ.get("CLIK_TMA", "0") == "1":
@@ -610,7 +616,9 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
         out.append("    const double* y, const double* x0, const unsigned* active0, double* sol, int* status,")
         out.append("    unsigned* active, int max_iter) {")
+        out.append("  clik::pdl_launch_dependents();")
         out.append("  clik::qp_step<Skill, clik::QP_FULL>(N, ld, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
+        out.append("  clik::pdl_wait();")
         out.append("}")
         if meta.get("qp_split"):
             # fast pass (working-set prediction only) + tail pass (full solver on what it left pending)
@@ -621,12 +629,16 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
             out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
             out.append("    const double* y, const double* x0, const unsigned* active0, double* sol, int* status,")
             out.append("    unsigned* active, int max_iter) {")
+            out.append("  clik::pdl_launch_dependents();")
             out.append("  clik::qp_step<Skill, clik::QP_FAST>(N, ld, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
+            out.append("  clik::pdl_wait();")
             out.append("}")
             out.append('extern "C" __global__ void %s clik_qp_tail_kernel(' % qbounds)
             out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
             out.append("    const double* y, const double* x0, const unsigned* active0, double* sol, int* status,")
             out.append("    unsigned* active, int max_iter) {")
+            out.append("  clik::pdl_launch_dependents();")
+            out.append("  clik::pdl_wait();   // reads the status[] / active[] the fast pass wrote")
             out.append("  clik::qp_step_tail<Skill>(N, ld, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
             out.append("}")
     qp_rollout = qp is not None and getattr(qp, "emit_rollout", True)

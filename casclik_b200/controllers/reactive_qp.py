@@ -219,7 +219,24 @@ class ReactiveQPController(BaseController):
         if dev not in self._compiled:
             self._compiled[dev] = runtime.CompiledSkill(self._cubin, self.kernel_meta,
                                                         n_slack=self.skill_spec.n_slack_var, device=dev)
+            if getattr(self, "_overlap", None) is not None:
+                self._compiled[dev].set_overlap(self._overlap)
         return self._compiled[dev]
+
+    def set_overlap(self, level):
+        """How successive solve_batch launches on one CUDA stream may overlap (include/clik.h,
+        clik_skill_set_overlap): 0 plain stream order, 1 (default) the two launches of one step overlap,
+        2 successive steps overlap as well — only for streams of independent batches (step k+1 must not
+        read what step k writes; closed loops belong in rollout_batch)."""
+        level = int(level)
+        if level not in (0, 1, 2):
+            raise ValueError("overlap level must be 0, 1 or 2")
+        self._overlap = level
+        if isinstance(self._compiled, dict):
+            for sk in self._compiled.values():
+                sk.set_overlap(level)
+        elif self._compiled is not None:
+            self._compiled.set_overlap(level)
 
     # ---- initial problem (virtual + slack with robot velocity fixed), reference :300-459 ---------------
     def setup_initial_problem_solver(self):

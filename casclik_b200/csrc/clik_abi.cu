@@ -96,6 +96,11 @@ struct clik_skill {
   int n_static = 1;           // statically compiled modes: where the group pass resumes the search
   ReadMask pinv_reads, qp_reads;
   bool use_tma = false;  // opt-in (CLIK_TMA=1): measured slower than the plain kernel, see DESIGN.md
+  // programmatic dependent launch (clik_skill_set_overlap / CLIK_PDL): 0 = plain stream order,
+  // 1 = the second launch of a two-launch step is scheduled while the first drains (it waits for the first
+  // to complete before it reads), 2 = also the first launch of a step, i.e. successive steps on one stream
+  // overlap tail and ramp — only for callers whose successive steps touch disjoint buffers
+  int overlap = 1;
   int sm_count = 0;
   std::mutex mu;  // guards scratch and the single-instance slot
   Scratch scratch;
@@ -108,6 +113,25 @@ struct clik_skill {
 };
 
 namespace {
+
+// One launch; `dependent` adds the programmatic-stream-serialization attribute (the kernel side is in
+// clik_math.cuh: griddepcontrol.launch_dependents at the start of every step kernel, griddepcontrol.wait
+// before the first dependent read or as the last action).
+cudaError_t launch(const KernelInfo& k, unsigned grid, void** args, cudaStream_t stream, bool dependent) {
+  if (!dependent)
+    return cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(k.block), args, 0, stream);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(k.block);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelExC(&cfg, (const void*)k.kernel, args);
+}
 
 clik_status setup_kernel(clik_skill* s, const char* name, KernelInfo* k) {
   cudaError_t e = cudaLibraryGetKernel(&k->kernel, s->lib, name);
@@ -422,9 +446,19 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
     delete s;
     return st;
   }
+  if (const char* e = getenv("CLIK_PDL")) s->overlap = std::max(0, std::min(2, atoi(e)));
   *out = s;
   return CLIK_OK;
 }
+
+clik_status clik_skill_set_overlap(clik_skill* s, int32_t level) {
+  if (!s) return fail(CLIK_ERR_INVALID, "skill is NULL");
+  if (level < 0 || level > 2) return fail(CLIK_ERR_INVALID, "overlap level %d (0, 1 or 2)", (int)level);
+  s->overlap = level;
+  return CLIK_OK;
+}
+
+int32_t clik_skill_get_overlap(const clik_skill* s) { return s ? s->overlap : -1; }
 
 void clik_skill_free(clik_skill* s) {
   if (!s) return;
@@ -452,9 +486,14 @@ clik_status clik_skill_launch_info(const clik_skill* s, int32_t which, int32_t* 
   return CLIK_OK;
 }
 
-clik_status clik_pinv_step_ld(const clik_skill* s, int64_t N, int64_t ld, const double* t, int32_t t_stride,
-                              const double* q, const double* x, const double* y, double* qdot,
-                              double* xdot, int32_t* mode, void* stream) {
+}  // extern "C"
+
+namespace {
+// `level`: overlap level of this call (the public entry points pass the skill's; the host-buffer pipelines,
+// which order copies and kernels on their own streams, never more than 1)
+clik_status pinv_step_impl(const clik_skill* s, int64_t N, int64_t ld, const double* t, int32_t t_stride,
+                           const double* q, const double* x, const double* y, double* qdot,
+                           double* xdot, int32_t* mode, void* stream, int level) {
   clik_status st = check_common(s, N, t, q, x, y);
   if (st != CLIK_OK || N == 0) return st;
   if (ld < N) return fail(CLIK_ERR_INVALID, "row stride ld (%lld) < N (%lld)", (long long)ld, (long long)N);
@@ -469,36 +508,43 @@ clik_status clik_pinv_step_ld(const clik_skill* s, int64_t N, int64_t ld, const 
   const bool tma_ok = s->use_tma && s->pinv_tma.kernel && (ld % 2 == 0) && aligned16(t) && aligned16(q) &&
                       aligned16(x) && aligned16(y);
   const int64_t tiles = (N + clik::PINV_TAIL_TILE - 1) / clik::PINV_TAIL_TILE;
+  const bool within = level >= 1, across = level >= 2;
   if (s->pinv_group_all && s->pinv_group.kernel) {
     // the whole step in the sub-warp mapping (from mode 0, every instance)
     int from = 0, pending_only = 0;
     void* gargs[] = {&n, &l, &t, &ts, &q, &x, &y, &qdot, &xdot, &mode, &from, &pending_only};
-    CK(cudaLaunchKernel((const void*)s->pinv_group.kernel, dim3((unsigned)std::min<int64_t>(tiles, 1 << 20)),
-                        dim3(s->pinv_group.block), gargs, 0, (cudaStream_t)stream));
+    CK(launch(s->pinv_group, (unsigned)std::min<int64_t>(tiles, 1 << 20), gargs, (cudaStream_t)stream, across));
   } else if (s->pinv_split && s->pinv_fast.kernel && s->pinv_group.kernel && mode != nullptr) {
     // two launches: statically compiled modes for every instance (thread mapping, registers), then the
     // run-time tail of the activation map for the instances they all rejected (sub-warp mapping);
     // handed over through mode[] (transient value PINV_PENDING)
-    CK(cudaLaunchKernel((const void*)s->pinv_fast.kernel, dim3(grid_for(s->pinv_fast, N)), dim3(s->pinv_fast.block),
-                        args, 0, (cudaStream_t)stream));
+    CK(launch(s->pinv_fast, grid_for(s->pinv_fast, N), args, (cudaStream_t)stream, across));
     int from = s->n_static, pending_only = 1;
     void* gargs[] = {&n, &l, &t, &ts, &q, &x, &y, &qdot, &xdot, &mode, &from, &pending_only};
-    CK(cudaLaunchKernel((const void*)s->pinv_group.kernel, dim3((unsigned)std::min<int64_t>(tiles, 1 << 20)),
-                        dim3(s->pinv_group.block), gargs, 0, (cudaStream_t)stream));
+    CK(launch(s->pinv_group, (unsigned)std::min<int64_t>(tiles, 1 << 20), gargs, (cudaStream_t)stream, within));
   } else if (tma_ok) {
     CK(cudaLaunchKernel((const void*)s->pinv_tma.kernel, dim3(balanced_grid(s->pinv_tma, N)),
                         dim3(s->pinv_tma.block), args, 0, (cudaStream_t)stream));
   } else {
-    CK(cudaLaunchKernel((const void*)s->pinv.kernel, dim3(grid_for(s->pinv, N)), dim3(s->pinv.block),
-                        args, 0, (cudaStream_t)stream));
+    CK(launch(s->pinv, grid_for(s->pinv, N), args, (cudaStream_t)stream, across));
   }
   return CLIK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+clik_status clik_pinv_step_ld(const clik_skill* s, int64_t N, int64_t ld, const double* t, int32_t t_stride,
+                              const double* q, const double* x, const double* y, double* qdot,
+                              double* xdot, int32_t* mode, void* stream) {
+  return pinv_step_impl(s, N, ld, t, t_stride, q, x, y, qdot, xdot, mode, stream, s ? s->overlap : 0);
 }
 
 clik_status clik_pinv_step(const clik_skill* s, int64_t N, const double* t, int32_t t_stride,
                            const double* q, const double* x, const double* y, double* qdot,
                            double* xdot, int32_t* mode, void* stream) {
-  return clik_pinv_step_ld(s, N, N, t, t_stride, q, x, y, qdot, xdot, mode, stream);
+  return pinv_step_impl(s, N, N, t, t_stride, q, x, y, qdot, xdot, mode, stream, s ? s->overlap : 0);
 }
 
 clik_status clik_pinv_rollout(const clik_skill* s, int64_t N, int32_t steps, double dt, const double* t0,
@@ -519,10 +565,13 @@ clik_status clik_pinv_rollout(const clik_skill* s, int64_t N, int32_t steps, dou
   return CLIK_OK;
 }
 
-clik_status clik_qp_step_ld(const clik_skill* s, int64_t N, int64_t ld, const double* t, int32_t t_stride,
-                            const double* q, const double* x, const double* y, const double* x0,
-                            const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
-                            int32_t max_iter, void* stream) {
+}  // extern "C"
+
+namespace {
+clik_status qp_step_impl(const clik_skill* s, int64_t N, int64_t ld, const double* t, int32_t t_stride,
+                         const double* q, const double* x, const double* y, const double* x0,
+                         const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
+                         int32_t max_iter, void* stream, int level) {
   clik_status st = check_common(s, N, t, q, x, y);
   if (st != CLIK_OK || N == 0) return st;
   if (ld < N) return fail(CLIK_ERR_INVALID, "row stride ld (%lld) < N (%lld)", (long long)ld, (long long)N);
@@ -533,27 +582,38 @@ clik_status clik_qp_step_ld(const clik_skill* s, int64_t N, int64_t ld, const do
   int ts = t_stride ? 1 : 0;
   int mi = max_iter > 0 ? max_iter : 10 * (s->desc.qp_n + s->desc.qp_m);
   void* args[] = {&n, &l, &t, &ts, &q, &x, &y, &x0, &active0, &sol, &status, &active, &mi};
+  const bool within = level >= 1, across = level >= 2;
   if (s->qp_fast.kernel && s->qp_tail.kernel && s->qp_split && status != nullptr) {
     // two launches: the working-set prediction for every instance (no Goldfarb-Idnani code in that
     // kernel: ~160 registers instead of 255 + spills), then the full solver for the few instances the
     // prediction could not certify; they are handed over through status[] (transient value 3).
-    CK(cudaLaunchKernel((const void*)s->qp_fast.kernel, dim3(grid_for(s->qp_fast, N)), dim3(s->qp_fast.block),
-                        args, 0, (cudaStream_t)stream));
+    CK(launch(s->qp_fast, grid_for(s->qp_fast, N), args, (cudaStream_t)stream, across));
     const int64_t tiles = (N + clik::QP_TAIL_TILE - 1) / clik::QP_TAIL_TILE;
-    CK(cudaLaunchKernel((const void*)s->qp_tail.kernel, dim3((unsigned)std::min<int64_t>(tiles, 1 << 20)),
-                        dim3(s->qp_tail.block), args, 0, (cudaStream_t)stream));
+    CK(launch(s->qp_tail, (unsigned)std::min<int64_t>(tiles, 1 << 20), args, (cudaStream_t)stream, within));
     return CLIK_OK;
   }
-  CK(cudaLaunchKernel((const void*)s->qp.kernel, dim3(grid_for(s->qp, N)), dim3(s->qp.block), args,
-                      0, (cudaStream_t)stream));
+  CK(launch(s->qp, grid_for(s->qp, N), args, (cudaStream_t)stream, across));
   return CLIK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+clik_status clik_qp_step_ld(const clik_skill* s, int64_t N, int64_t ld, const double* t, int32_t t_stride,
+                            const double* q, const double* x, const double* y, const double* x0,
+                            const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
+                            int32_t max_iter, void* stream) {
+  return qp_step_impl(s, N, ld, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter, stream,
+                      s ? s->overlap : 0);
 }
 
 clik_status clik_qp_step(const clik_skill* s, int64_t N, const double* t, int32_t t_stride,
                          const double* q, const double* x, const double* y, const double* x0,
                          const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
                          int32_t max_iter, void* stream) {
-  return clik_qp_step_ld(s, N, N, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter, stream);
+  return qp_step_impl(s, N, N, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter, stream,
+                      s ? s->overlap : 0);
 }
 
 clik_status clik_qp_rollout(const clik_skill* s, int64_t N, int32_t steps, double dt, const double* t0,
@@ -621,9 +681,9 @@ clik_status pinv_host_range(clik_skill* s, int64_t N, int64_t lo, int64_t cnt, c
       clik_status zs = ensure_scratch(s, 0, 256);
       if (zs != CLIK_OK) return zs;
       auto off = [lo](const void* p) { return p ? (const double*)p + lo : nullptr; };
-      zs = clik_pinv_step_ld(s, cnt, N, t_stride ? off(dt) : (const double*)dt, t_stride, off(dq), off(dx),
-                             off(dy), (double*)off(dqd), (double*)off(dxd),
-                             dm ? (int32_t*)dm + lo : nullptr, s->scratch.stream[0]);
+      zs = pinv_step_impl(s, cnt, N, t_stride ? off(dt) : (const double*)dt, t_stride, off(dq), off(dx),
+                          off(dy), (double*)off(dqd), (double*)off(dxd),
+                          dm ? (int32_t*)dm + lo : nullptr, s->scratch.stream[0], std::min(s->overlap, 1));
       if (zs != CLIK_OK) return zs;
       CK(cudaStreamSynchronize(s->scratch.stream[0]));
       return CLIK_OK;
@@ -642,13 +702,13 @@ clik_status pinv_host_range(clik_skill* s, int64_t N, int64_t lo, int64_t cnt, c
   f.push_back({nullptr, d.n_virtual ? xdot : nullptr, d.n_virtual, 8, 1, 0});
   f.push_back({nullptr, mode, 1, 4, 1, 0});
   return run_host_pipeline(s, N, lo, cnt, f, [&](char* base, int64_t c, cudaStream_t stream) {
-    return clik_pinv_step(s, c, (const double*)(base + f[0].dev_off), t_stride,
+    return pinv_step_impl(s, c, c, (const double*)(base + f[0].dev_off), t_stride,
                           (const double*)(base + f[1].dev_off),
                           d.n_virtual ? (const double*)(base + f[2].dev_off) : nullptr,
                           d.n_input ? (const double*)(base + f[3].dev_off) : nullptr,
                           (double*)(base + f[4].dev_off),
                           d.n_virtual ? (double*)(base + f[5].dev_off) : nullptr,
-                          mode ? (int32_t*)(base + f[6].dev_off) : nullptr, stream);
+                          mode ? (int32_t*)(base + f[6].dev_off) : nullptr, stream, std::min(s->overlap, 1));
   });
 }
 
@@ -668,10 +728,10 @@ clik_status qp_host_range(clik_skill* s, int64_t N, int64_t lo, int64_t cnt, con
       clik_status zs = ensure_scratch(s, 0, 256);
       if (zs != CLIK_OK) return zs;
       auto off = [lo](const void* p) { return p ? (const double*)p + lo : nullptr; };
-      zs = clik_qp_step_ld(s, cnt, N, t_stride ? off(dt) : (const double*)dt, t_stride, off(dq), off(dx), off(dy),
-                           off(dx0), da0 ? (const uint32_t*)da0 + lo : nullptr, (double*)off(dsol),
-                           dst ? (int32_t*)dst + lo : nullptr, dact ? (uint32_t*)dact + lo : nullptr, max_iter,
-                           s->scratch.stream[0]);
+      zs = qp_step_impl(s, cnt, N, t_stride ? off(dt) : (const double*)dt, t_stride, off(dq), off(dx), off(dy),
+                        off(dx0), da0 ? (const uint32_t*)da0 + lo : nullptr, (double*)off(dsol),
+                        dst ? (int32_t*)dst + lo : nullptr, dact ? (uint32_t*)dact + lo : nullptr, max_iter,
+                        s->scratch.stream[0], std::min(s->overlap, 1));
       if (zs != CLIK_OK) return zs;
       CK(cudaStreamSynchronize(s->scratch.stream[0]));
       return CLIK_OK;
@@ -692,7 +752,7 @@ clik_status qp_host_range(clik_skill* s, int64_t N, int64_t lo, int64_t cnt, con
   f.push_back({nullptr, active, 2, 4, 1, 0});
   f.push_back({active0, nullptr, 2, 4, 1, 0});
   return run_host_pipeline(s, N, lo, cnt, f, [&](char* base, int64_t c, cudaStream_t stream) {
-    return clik_qp_step(s, c, (const double*)(base + f[0].dev_off), t_stride,
+    return qp_step_impl(s, c, c, (const double*)(base + f[0].dev_off), t_stride,
                         (const double*)(base + f[1].dev_off),
                         d.n_virtual ? (const double*)(base + f[2].dev_off) : nullptr,
                         d.n_input ? (const double*)(base + f[3].dev_off) : nullptr,
@@ -700,7 +760,8 @@ clik_status qp_host_range(clik_skill* s, int64_t N, int64_t lo, int64_t cnt, con
                         active0 ? (const uint32_t*)(base + f[8].dev_off) : nullptr,
                         (double*)(base + f[5].dev_off),
                         status ? (int32_t*)(base + f[6].dev_off) : nullptr,
-                        active ? (uint32_t*)(base + f[7].dev_off) : nullptr, max_iter, stream);
+                        active ? (uint32_t*)(base + f[7].dev_off) : nullptr, max_iter, stream,
+                        std::min(s->overlap, 1));
   });
 }
 

@@ -15,6 +15,24 @@
 
 namespace clik {
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
+// attribute may begin while its predecessor on the stream is still draining.  Every step kernel tells the
+// hardware at its start that a successor may be scheduled (free when nothing asks for it) and — as its last
+// action, or before its first read when it consumes the predecessor's output — waits for the predecessor to
+// have completed and flushed, so kernels still complete in stream order.  Both are no-ops in a launch without
+// the attribute; clik_abi.cu sets it only where the caller declared launches independent
+// (clik_skill_set_overlap) and between the two launches of one step.
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 __constant__ double SC_TAB[20] = {
     6.36619772367581382433e-01,   // 0  2/pi
     1.57079632679489655800e+00,   // 1  pi/2 hi

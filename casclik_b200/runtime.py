@@ -34,7 +34,7 @@ EXPORTS = (
     "clik_qp_rollout", "clik_qp_dense",
     "clik_pinv_step_host", "clik_qp_step_host", "clik_skill_launch_info",
     "clik_pinv_step_ld", "clik_qp_step_ld", "clik_pinv_step_host_multi", "clik_qp_step_host_multi",
-    "clik_pinv_solve_one", "clik_qp_solve_one",
+    "clik_pinv_solve_one", "clik_qp_solve_one", "clik_skill_set_overlap", "clik_skill_get_overlap",
     "clik_measure_fp64_peak", "clik_flush_l2", "clik_device_count", "clik_abi_version",
     "clik_last_error",
 )
@@ -100,6 +100,10 @@ def load_library():
     lib.clik_qp_dense.argtypes = [i32, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.clik_skill_launch_info.restype = i32
     lib.clik_skill_launch_info.argtypes = [vp, i32, _c_int32_p, _c_int32_p, _c_int32_p, _c_int32_p]
+    lib.clik_skill_set_overlap.restype = i32
+    lib.clik_skill_set_overlap.argtypes = [vp, i32]
+    lib.clik_skill_get_overlap.restype = i32
+    lib.clik_skill_get_overlap.argtypes = [vp]
     lib.clik_measure_fp64_peak.restype = i32
     lib.clik_measure_fp64_peak.argtypes = [i32, i32, _c_double_p]
     lib.clik_flush_l2.restype = i32
@@ -226,6 +230,15 @@ class CompiledSkill(object):
                 self.handle = None
         except Exception:
             pass
+
+    def set_overlap(self, level):
+        """0: plain stream order; 1 (default): the second launch of a two-launch step is scheduled while
+        the first drains; 2: successive step launches on one stream are declared independent (disjoint
+        buffers) and may overlap tail and ramp (programmatic dependent launch; include/clik.h)."""
+        check(self._lib.clik_skill_set_overlap(self.handle, int(level)))
+
+    def overlap(self):
+        return int(self._lib.clik_skill_get_overlap(self.handle))
 
     def launch_info(self, which=0):
         g, b, r, l = (ctypes.c_int32() for _ in range(4))

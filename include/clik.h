@@ -191,6 +191,23 @@ clik_status clik_qp_step_host_multi(const clik_skill* const* skills, int32_t n_s
                                     const double* y, const double* x0, const uint32_t* active0,
                                     double* sol, int32_t* status, uint32_t* active, int32_t max_iter);
 
+/* Overlap of launches on one stream (programmatic dependent launch, sm_90+; replaces nothing in the
+ * reference — its loop is sequential, casclik/controllers/pseudo_inverse.py:512-556 — it is the batched
+ * counterpart of calling solve() back to back).
+ *   0  plain stream order: a launch starts when everything before it on the stream has completed;
+ *   1  (default) the second launch of a two-launch step (QP fast + tail pass, pinv fast + group pass) is
+ *      scheduled while the first drains and waits on the device for it to complete before it reads —
+ *      same results, same ordering towards everything else on the stream;
+ *   2  additionally the FIRST launch of every clik_pinv_step* / clik_qp_step* call may begin while the
+ *      previous kernel on the stream is still draining (its last CTAs running).  The caller thereby declares
+ *      that the call does not read what the previous launch on the stream writes and does not write what it
+ *      reads (a stream of independent batches).  Kernels still COMPLETE in stream order, so events,
+ *      copies and any kernel launched without this level keep their usual meaning.  Never use it when step
+ *      k+1 consumes step k's output through device memory (use the rollout entry points for closed loops).
+ * CLIK_PDL=<level> in the environment sets the level at load time. */
+clik_status clik_skill_set_overlap(clik_skill* skill, int32_t level);
+int32_t clik_skill_get_overlap(const clik_skill* skill);
+
 /* Launch geometry chosen at load time (for reporting). */
 clik_status clik_skill_launch_info(const clik_skill* skill, int32_t which /*0 pinv, 1 qp, 2 pinv TMA-staged, 3 qp fast pass, 4 qp tail pass, 5 pinv fast pass, 6 pinv group pass*/,
                                    int32_t* grid, int32_t* block, int32_t* regs_per_thread,

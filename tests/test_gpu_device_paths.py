@@ -410,3 +410,45 @@ def test_sub_warp_mapping_on_the_benchmark_skills_gpu(monkeypatch):
         assert np.array_equal(mode, ref_mode), name
         nerr = np.linalg.norm(v - ref_v, axis=0) / np.maximum(np.linalg.norm(ref_v, axis=0), 1e-300)
         assert close(v, ref_v, RTOL, ATOL).mean() > 0.999 and nerr.max() < 1e-9, (name, nerr.max())
+
+
+@pytest.mark.parametrize("name,env", [("ur5_track", {}), ("ur5_moe2016_pinv", {}), ("iiwa_multitask", {"CLIK_UNIT_SETS": "0"}),
+                                      ("ur5_qp", {}), ("ur5_moe2016_qp", {})],
+                         ids=["ur5_track", "moe_pinv", "iiwa_fast_plus_group", "ur5_qp_fast_plus_tail", "moe_qp"])
+def test_overlapped_launches_give_the_bits_of_plain_stream_order(name, env, monkeypatch):
+    """clik_skill_set_overlap (programmatic dependent launch): a stream of independent batches launched
+    back to back with level 2 (steps overlap tail and ramp), level 1 (the two launches of one step
+    overlap) and level 0 (plain stream order) must give identical bits for every batch, and a plain
+    kernel launched behind them must see all of their output (completion stays in stream order)."""
+    torch = _torch()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    sc = scenarios.get(name)
+    ctrl = sc.make_controller()
+    ctrl.setup_solver()
+    is_qp = sc.controller == "qp"
+    N, sets = 300_001, 6                                  # ragged size, several batches in flight
+    ins = []
+    for s in range(sets):
+        inp = sc.sample(N, seed=40 + s)
+        ins.append(tuple(_up(inp.get(k)) for k in ("t", "q", "x", "y")))
+    results = {}
+    for level in (0, 1, 2):
+        ctrl.set_overlap(level)
+        assert ctrl._skill(0).overlap() == level
+        outs = []
+        for rep in range(3):                              # the same buffers are overwritten three times
+            outs = [ctrl.solve_batch(*ins[s]) if rep == 0 else ctrl.solve_batch(*ins[s], out=outs[s]) for s in range(sets)]
+        # an ordinary torch kernel behind the last step: sums every output of every batch
+        sums = [sum(float(o.double().sum()) for o in out if o is not None) for out in outs]
+        torch.cuda.synchronize()
+        results[level] = ([tuple(None if o is None else o.cpu().numpy().copy() for o in out) for out in outs], sums)
+    ref, ref_sums = results[0]
+    for level in (1, 2):
+        got, sums = results[level]
+        for s in range(sets):
+            for a, b in zip(got[s], ref[s]):
+                assert (a is None and b is None) or np.array_equal(a, b, equal_nan=True), (level, s)
+        assert sums == ref_sums
+    if is_qp:
+        assert np.all(ref[0][1] == runtime.QP_SOLVED)
