@@ -231,12 +231,16 @@ def _launches_per_step(meta, is_qp):
     return 2 if (meta.get("pinv_split") and os.environ.get("CLIK_PINV_SPLIT", "1") != "0") else 1
 
 
-def _overlap_note(level):
-    return {0: "0: plain stream order",
-            1: "1: plain stream order between steps (the two launches of a two-launch step overlap)",
-            2: "2: the K steps are independent batches on disjoint buffers; a step kernel may start while the "
-               "previous one drains (programmatic dependent launch), completion stays in stream order; "
-               "`stream_ordered` is the same loop without it"}[level]
+def _overlap_note(level, streams=1):
+    note = {0: "0: plain stream order on each stream",
+            1: "1: plain stream order between the steps of a stream (the two launches of a two-launch step overlap)",
+            2: "2: a step kernel may start while the previous one on its stream drains (programmatic "
+               "dependent launch; the steps are independent batches on disjoint buffers, completion stays in "
+               "stream order)"}[level]
+    if streams > 1:
+        note += "; the K independent batches alternate over %d CUDA streams (forked from / joined into the " \
+                "timed stream), so the drain of one step overlaps the ramp of the next" % streams
+    return note + "; `stream_ordered` is the same K steps on one stream, one kernel after the other"
 
 
 def _bytes_per_set(meta, is_qp, B):
@@ -244,7 +248,7 @@ def _bytes_per_set(meta, is_qp, B):
 
 
 def time_device_resident(torch, dist, ctrl, scenario, B, steps, warm, rank, world, dev, min_sets=2,
-                         seed_base=1000, overlap=2, plain_too=True):
+                         seed_base=1000, overlap=2, plain_too=True, n_streams=1):
     """K steps of solve_batch on device-resident inputs -> (ms total max-over-ranks, n_sets, graph?, step,
     ms of the same K steps in plain stream order | None).
     Inputs and outputs rotate over enough sets to exceed L2 twice over."""
@@ -252,6 +256,9 @@ def time_device_resident(torch, dist, ctrl, scenario, B, steps, warm, rank, worl
     is_qp = scenario.controller == "qp"
     per_set = _bytes_per_set(meta, is_qp, B)
     n_sets = int(max(min_sets, min(16, -(-(300 << 20) // max(per_set, 1)))))
+    n_streams = max(1, int(n_streams))
+    n_sets = -(-n_sets // n_streams) * n_streams      # buffer set k always travels on stream k % n_streams
+    side = [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
     ins, outs = [], []
     for s in range(n_sets):
         inp = scenario.sample(B, seed=seed_base * (rank + 1) + s)
@@ -271,6 +278,26 @@ def time_device_resident(torch, dist, ctrl, scenario, B, steps, warm, rank, worl
         t, q, x, y = ins[i % n_sets]
         ctrl.solve_batch(t, q, x, y, out=outs[i % n_sets])
 
+    def run_steps(k):
+        """k steps; with several streams, independent batches alternate over them (fork from / join into
+        the current stream, so events recorded on it bracket all of the work — also under graph capture)."""
+        if not side:
+            for i in range(k):
+                step(i)
+            return
+        main = torch.cuda.current_stream()
+        for st in side:
+            st.wait_stream(main)
+        for i in range(k):
+            j = (i % n_sets) % n_streams
+            if j == 0:
+                step(i)
+            else:
+                with torch.cuda.stream(side[j - 1]):
+                    step(i)
+        for st in side:
+            main.wait_stream(st)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -279,8 +306,7 @@ def time_device_resident(torch, dist, ctrl, scenario, B, steps, warm, rank, worl
     def timed(level):
         """K timed steps at overlap level `level` -> (ms max-over-ranks, replayed from a graph?)."""
         ctrl.set_overlap(level)
-        for i in range(max(warm, 3)):
-            step(i)
+        run_steps(max(warm, 3))
         barrier()
         # The K timed steps are K launches of the step kernel through the C ABI.  They are captured once
         # into a CUDA graph and replayed, so that host jitter (8 ranks sharing the box's cores with the
@@ -290,8 +316,7 @@ def time_device_resident(torch, dist, ctrl, scenario, B, steps, warm, rank, worl
             try:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    for i in range(steps):
-                        step(i)
+                    run_steps(steps)
                 g.replay()                       # untimed: uploads the graph
                 graph = g
             except Exception as exc:             # capture not possible: time the plain launch loop
@@ -304,8 +329,7 @@ def time_device_resident(torch, dist, ctrl, scenario, B, steps, warm, rank, worl
         if graph is not None:
             graph.replay()
         else:
-            for i in range(steps):
-                step(i)
+            run_steps(steps)
         e1.record()
         barrier()
         tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -313,13 +337,16 @@ def time_device_resident(torch, dist, ctrl, scenario, B, steps, warm, rank, worl
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         return float(tms.item()), graph is not None
 
-    # The K steps are K independent batches (disjoint rotating buffers), so the stream may overlap the
-    # tail of one step kernel with the ramp of the next (programmatic dependent launch, overlap level 2:
-    # include/clik.h clik_skill_set_overlap; kernels still complete in stream order).  The same K steps in
-    # plain stream order (level 1) are timed as well and reported next to the value.
+    # The K steps are K independent batches (disjoint rotating buffers).  By default they alternate over two
+    # CUDA streams, so the drain of one step kernel (and the latency-bound tail pass of a QP step) overlaps
+    # the ramp of the next batch; on one stream the same is available as overlap level 2 (programmatic
+    # dependent launch, include/clik.h clik_skill_set_overlap).  The same K steps on one stream in plain
+    # stream order are timed as well and reported next to the value (`stream_ordered`).
     ms_plain = None
-    if overlap >= 2 and plain_too:
-        ms_plain, _ = timed(1)
+    if (overlap >= 2 or side) and plain_too:
+        keep, side[:] = list(side), []
+        ms_plain, _ = timed(min(overlap, 1))
+        side[:] = keep
     ms, graphed = timed(overlap)
     return ms, n_sets, graphed, step, ms_plain
 
@@ -372,7 +399,9 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 20, help="instances per GPU per step")
     ap.add_argument("--sets", type=int, default=0, help="resident input/output sets rotated over (0 = enough for 300 MB)")
     ap.add_argument("--e2e-steps", type=int, default=20)
-    ap.add_argument("--overlap", type=int, default=int(os.environ.get("CLIK_PDL", "2")), choices=[0, 1, 2],
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("CLIK_BENCH_STREAMS", "2")),
+                    help="CUDA streams the K independent batches of the device-resident loop alternate over")
+    ap.add_argument("--overlap", type=int, default=int(os.environ.get("CLIK_PDL", "1")), choices=[0, 1, 2],
                     help="clik_skill_set_overlap level of the device-resident loop (2: independent steps overlap)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs")
@@ -429,12 +458,13 @@ def main():
         per = _bytes_per_set(c.kernel_meta, qp, Bs)
         k = int(max(8, min(100, (3 << 30) // max(per, 1))))          # ~3 GB of algorithmic traffic per leg
         ms_tot, n_sets, graphed, _, ms_plain = time_device_resident(torch, dist, c, sc, Bs, k, 3, rank, world, dev,
-                                                                    seed_base=2000, overlap=args.overlap)
+                                                                    seed_base=2000, overlap=args.overlap,
+                                                                    n_streams=args.streams)
         total = batch if mode == "strong" else batch * world
         val = total * k / (ms_tot * 1e-3)
         out = {"config": cfg, "workload": sc.description, "value": val, "unit": UNIT,
                "ms_per_step": ms_tot / k, "steps": k, "batch_per_gpu": Bs, "global_batch": total,
-               "scaling": mode, "sets_rotated": n_sets, "overlap": _overlap_note(args.overlap),
+               "scaling": mode, "sets_rotated": n_sets, "overlap": _overlap_note(args.overlap, args.streams), "streams": args.streams,
                "gpu_launches": k * _launches_per_step(c.kernel_meta, qp)}
         if ms_plain is not None:
             out["stream_ordered"] = {"value": total * k / (ms_plain * 1e-3), "ms_per_step": ms_plain / k}
@@ -465,7 +495,7 @@ def main():
     sampler.start()
     ms, n_sets, graphed, step, ms_plain = time_device_resident(torch, dist, ctrl, scenario, B, args.steps, args.warmup,
                                                                rank, world, dev, min_sets=max(args.sets, 2),
-                                                               overlap=args.overlap)
+                                                               overlap=args.overlap, n_streams=args.streams)
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- end to end through the host-buffer C ABI (pinned host inputs, copies inside) --------------
@@ -534,7 +564,7 @@ def main():
                        "parallelism": "independent shards, one per GPU, no collective on the data path",
                        "launch_mode": ("%d step-kernel launches replayed from one CUDA graph" % args.steps
                                        if graphed else "direct launches"),
-                       "overlap": _overlap_note(args.overlap),
+                       "overlap": _overlap_note(args.overlap, args.streams), "streams": args.streams,
                        "host_affinity": ("rank 0 bound to its GPU's NUMA node: %d of %d CPUs" % (len(numa[1]), len(numa[0]))
                                          if numa else "unbound"),
                        "l2": "rotating %d resident input + output sets (%d MB of algorithmic traffic in total) "

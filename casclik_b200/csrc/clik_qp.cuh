@@ -631,6 +631,9 @@ constexpr int CRASH_PASSES = 12;
 // the Goldfarb-Idnani iteration, whose single-thread latency (~30 us with its spills) was the whole
 // duration of the tail launch.
 constexpr int CRASH_SINGLE_PASSES = 30;
+#ifdef CLIK_QP_STATS
+static long long qp_pass_hist[2][64];   // host-harness instrumentation (tools/qp_pass_stats.py): passes per call [all-at-once / one-row]
+#endif
 template <class S, int MAXP = CRASH_PASSES, bool SINGLE = false>
 __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*in: guess, out*/,
                                             unsigned* lo, double (&xout)[S::QN], bool* still_changing = nullptr) {
@@ -821,6 +824,9 @@ __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*
     if (still_changing != nullptr) *still_changing = changed;
 #pragma unroll
     for (int j = 0; j < NX; ++j) xout[j] = xc[j];
+#ifdef CLIK_QP_STATS
+    if (!changed || pass == MAXP - 1) ++qp_pass_hist[SINGLE ? 1 : 0][pass + 1 < 64 ? pass + 1 : 63];
+#endif
     if (!__any_sync(__activemask(), changed)) break;
   }
   unsigned mu = 0u, ml = 0u;
