@@ -112,6 +112,10 @@ def _launch_info(ctrl, is_qp):
         if ctrl.kernel_meta.get("qp_split") and os.environ.get("CLIK_QP_SPLIT", "1") != "0":
             info = {"fast": sk.launch_info(3), "tail": sk.launch_info(4), "full (status == NULL)": info,
                     "used": "fast + tail"}
+            try:
+                info["tail, capped (batches with more tail tiles than resident tail CTAs)"] = sk.launch_info(7)
+            except Exception:
+                pass
         return info
     info = {"plain": sk.launch_info(0)}
     try:

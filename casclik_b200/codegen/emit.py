@@ -518,6 +518,8 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
                        ("true" if os.environ.get("CLIK_QP_CRASH_SINGLE", "1") == "1" else "false"))
             out.append("  static constexpr int QP_FAST_PASSES = %d;   // prediction passes in the fast launch (the tail continues)" %
                        int(os.environ.get("CLIK_QP_FAST_PASSES", "4")))
+            out.append("  static constexpr int QP_FLIP_PASSES = %d;   // first passes in which a released variable may go straight to another bound" %
+                       int(os.environ.get("CLIK_QP_FLIP_PASSES", "2")))
             out.append("  static constexpr bool QP_EQ_START = %s;" %
                        ("true" if os.environ.get("CLIK_QP_EQ_START", "0") == "1" else "false"))
             out.append(_switch("dense_row", qp.dense_rows or [0]))
@@ -641,6 +643,21 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
             out.append("  clik::pdl_wait();   // reads the status[] / active[] the fast pass wrote")
             out.append("  clik::qp_step_tail<Skill>(N, ld, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
             out.append("}")
+            # the same tail pass capped to 4 CTAs per SM (128 registers, the iteration spills): chosen by the
+            # host for batches with more tail tiles than the uncapped kernel keeps resident — there the
+            # tail is a throughput problem (more CTAs in flight, and its CTAs fit the hole a finished fast-pass
+            # CTA of another stream leaves), for small batches it is the latency of the slowest instance
+            tcap = int(os.environ.get("CLIK_QP_TAIL_CAP", "4"))
+            meta["qp_tail_cap"] = tcap
+            if tcap > 0:
+                out.append('extern "C" __global__ void __launch_bounds__(%d, %d) clik_qp_tail_capped_kernel(' % (block_threads, tcap))
+                out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
+                out.append("    const double* y, const double* x0, const unsigned* active0, double* sol, int* status,")
+                out.append("    unsigned* active, int max_iter) {")
+                out.append("  clik::pdl_launch_dependents();")
+                out.append("  clik::pdl_wait();")
+                out.append("  clik::qp_step_tail<Skill>(N, ld, t, t_stride, q, x, y, x0, active0, sol, status, active, max_iter);")
+                out.append("}")
     qp_rollout = qp is not None and getattr(qp, "emit_rollout", True)
     if qp_rollout:
         out.append('extern "C" __global__ void __launch_bounds__(%d) clik_qp_rollout_kernel(' % block_threads)
@@ -656,8 +673,9 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
         flags |= (32 if meta.get("pinv_group") else 0) | (64 if meta.get("pinv_split") else 0)
     if qp is not None:
         flags |= (4 if qp_rollout else 0) | (16 if meta.get("qp_split") else 0)
+        flags |= 128 if (meta.get("qp_split") and meta.get("qp_tail_cap", 0) > 0) else 0
     out.append("  // manifest: sizes, unroll, optional-kernel flags (1 pinv TMA, 2 pinv rollout, 4 QP rollout, 16 QP fast + tail pair,")
-    out.append("  // 32 pinv group kernel, 64 pinv fast kernel); o[16] statically compiled modes, o[17] block size of the group kernel")
+    out.append("  // 32 pinv group kernel, 64 pinv fast kernel, 128 capped QP tail kernel); o[16] statically compiled modes, o[17] block size of the group kernel")
     out.append("  o[0] = %d; o[1] = %d; o[2] = %d; o[3] = %d; o[4] = %d; o[5] = %d; o[6] = %d; o[7] = %d;"
                % (nq, nxv, ny, meta["n_modes"], meta["qp_n"], meta["qp_m"], meta.get("pinv_unroll", 1), flags))
     full = (1, 0xffffffff, 0xffffffff, 0xffffffff)

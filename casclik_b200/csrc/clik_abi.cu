@@ -89,8 +89,9 @@ struct ReadMask {
 struct clik_skill {
   clik_skill_desc desc;
   cudaLibrary_t lib = nullptr;
-  KernelInfo pinv, pinv_tma, pinv_rollout, pinv_fast, pinv_group, qp, qp_fast, qp_tail, qp_rollout;
+  KernelInfo pinv, pinv_tma, pinv_rollout, pinv_fast, pinv_group, qp, qp_fast, qp_tail, qp_tail_capped, qp_rollout;
   bool qp_split = true;  // CLIK_QP_SPLIT=0: always the single full kernel
+  int qp_tail_pick = -1; // CLIK_QP_TAIL_PICK: 0 always the uncapped tail kernel, 1 always the capped one, -1 by batch size
   bool pinv_split = true;     // CLIK_PINV_SPLIT=0: run-time mode tail inside the one kernel (thread mapping)
   bool pinv_group_all = false;  // CLIK_PINV_GROUP=1: whole batches through the sub-warp mapping (A/B measurements)
   int n_static = 1;           // statically compiled modes: where the group pass resumes the search
@@ -439,6 +440,8 @@ clik_status clik_skill_load(const void* cubin, size_t len, const clik_skill_desc
     if (flags & 4) st = setup_kernel(s, "clik_qp_rollout_kernel", &s->qp_rollout);
     if (st == CLIK_OK && (flags & 16)) st = setup_kernel(s, "clik_qp_fast_kernel", &s->qp_fast);
     if (st == CLIK_OK && (flags & 16)) st = setup_kernel(s, "clik_qp_tail_kernel", &s->qp_tail);
+    if (st == CLIK_OK && (flags & 128)) st = setup_kernel(s, "clik_qp_tail_capped_kernel", &s->qp_tail_capped);
+    if (const char* e = getenv("CLIK_QP_TAIL_PICK")) s->qp_tail_pick = atoi(e);
     if (const char* e = getenv("CLIK_QP_SPLIT")) s->qp_split = atoi(e) != 0;
   }
   if (st != CLIK_OK) {
@@ -477,7 +480,7 @@ clik_status clik_skill_launch_info(const clik_skill* s, int32_t which, int32_t* 
                                    int32_t* regs, int32_t* local_bytes) {
   if (!s) return fail(CLIK_ERR_INVALID, "skill is NULL");
   const KernelInfo& k = which == 0 ? s->pinv : which == 2 ? s->pinv_tma : which == 3 ? s->qp_fast : which == 4 ? s->qp_tail
-                        : which == 5 ? s->pinv_fast : which == 6 ? s->pinv_group : s->qp;
+                        : which == 5 ? s->pinv_fast : which == 6 ? s->pinv_group : which == 7 ? s->qp_tail_capped : s->qp;
   if (!k.kernel) return fail(CLIK_ERR_INVALID, "skill has no such kernel");
   if (grid) *grid = k.grid;
   if (block) *block = k.block;
@@ -589,7 +592,13 @@ clik_status qp_step_impl(const clik_skill* s, int64_t N, int64_t ld, const doubl
     // prediction could not certify; they are handed over through status[] (transient value 3).
     CK(launch(s->qp_fast, grid_for(s->qp_fast, N), args, (cudaStream_t)stream, across));
     const int64_t tiles = (N + clik::QP_TAIL_TILE - 1) / clik::QP_TAIL_TILE;
-    CK(launch(s->qp_tail, (unsigned)std::min<int64_t>(tiles, 1 << 20), args, (cudaStream_t)stream, within));
+    // small batches (every tail CTA resident at once): the launch lasts as long as its slowest instance, which
+    // the uncapped kernel (255 registers) runs fastest; more tiles than that: a throughput problem, the capped
+    // kernel keeps twice the CTAs in flight and interleaves with other streams' fast passes (profiles/r2_ab10.txt)
+    const bool capped = s->qp_tail_capped.kernel &&
+                        (s->qp_tail_pick >= 0 ? s->qp_tail_pick != 0 : tiles > s->qp_tail.resident);
+    CK(launch(capped ? s->qp_tail_capped : s->qp_tail, (unsigned)std::min<int64_t>(tiles, 1 << 20), args,
+              (cudaStream_t)stream, within));
     return CLIK_OK;
   }
   CK(launch(s->qp, grid_for(s->qp, N), args, (cudaStream_t)stream, across));

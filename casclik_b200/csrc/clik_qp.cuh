@@ -748,12 +748,24 @@ __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*
       const double gk = gs[c] * S::unit_coef(i);
       nf[c] = (fr[c] == i + 1 && gk <= 0.0) ? i + 1 : ((fr[c] == -(i + 1) && gk >= 0.0) ? -(i + 1) : nf[c]);
     }
+    // A fixed variable whose multiplier has the wrong sign is released — and in the first passes tested at
+    // the value it would take if it were free with the dense multipliers as they are (xfree): when that lies
+    // beyond one of its bounds (typically the opposite one: the first pass clamps every joint at the sign of
+    // the unconstrained optimum, and a far target turns some of them around) the variable moves to that bound
+    // in this pass instead of going through "free" first.  For the UR5 problem this takes the mean number
+    // of passes from 3.6 to 2.8 and the share of instances final after 3 passes from 40 % to 91 %
+    // (profiles/r2_qp_pass_stats.txt).  Only a guess changes: every set is still certified by a pass that
+    // leaves it unchanged.  Later passes release to "free" (a two-bound flip-flop cannot form).
+    double xt[NX];
+    const bool flip = !SINGLE && pass < S::QP_FLIP_PASSES;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) xt[j] = (flip && fr[j] != 0 && nf[j] == 0) ? xc[j] - gs[j] : xc[j];
 #pragma unroll
     for (int i = 0; i < MU; ++i) {
       constexpr double one = 1.0;
       const int c = S::unit_col(i);
       const double ik = one / (S::unit_coef(i) < 0.0 ? -S::unit_coef(i) : S::unit_coef(i));
-      const double r = S::unit_coef(i) * xc[c];
+      const double r = S::unit_coef(i) * xt[c];
       const double vu = (r - D.ubu[i]) * ik, vl = (D.lbu[i] - r) * ik;
       if (S::unit_row(i) < 32) {
         if (vu > 1e-12 * fmax(1.0, fabs(D.ubu[i])) * ik && vu > viol[c]) { viol[c] = vu; nf[c] = i + 1; }

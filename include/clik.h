@@ -209,7 +209,7 @@ clik_status clik_skill_set_overlap(clik_skill* skill, int32_t level);
 int32_t clik_skill_get_overlap(const clik_skill* skill);
 
 /* Launch geometry chosen at load time (for reporting). */
-clik_status clik_skill_launch_info(const clik_skill* skill, int32_t which /*0 pinv, 1 qp, 2 pinv TMA-staged, 3 qp fast pass, 4 qp tail pass, 5 pinv fast pass, 6 pinv group pass*/,
+clik_status clik_skill_launch_info(const clik_skill* skill, int32_t which /*0 pinv, 1 qp, 2 pinv TMA-staged, 3 qp fast pass, 4 qp tail pass, 5 pinv fast pass, 6 pinv group pass, 7 qp tail pass capped to 4 CTAs/SM (large batches)*/,
                                    int32_t* grid, int32_t* block, int32_t* regs_per_thread,
                                    int32_t* local_bytes_per_thread);
 

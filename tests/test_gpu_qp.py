@@ -300,6 +300,31 @@ def test_two_launch_split_equals_the_single_kernel(monkeypatch):
     assert int(outs["1"][0][1].abs().sum()) == 0          # every status final (0), none left pending
 
 
+@pytest.mark.parametrize("name", ["ur5_qp", "ur5_moe2016_qp"])
+def test_capped_tail_kernel_gives_the_bits_of_the_uncapped_one(name, monkeypatch):
+    """The tail pass exists twice — natural register allocation, and capped to 4 CTAs per SM for batches with
+    more tail tiles than resident tail CTAs (clik_abi.cu picks by batch size; CLIK_QP_TAIL_PICK forces one).
+    Same source, different register allocation: identical results, and the default pick is one of them."""
+    torch = _torch()
+    sc = scenarios.get(name)
+    N = 40_000 + 11
+    inp = sc.sample(N, seed=12)
+    dev = {k: (None if v is None else torch.from_numpy(np.ascontiguousarray(v)).cuda()) for k, v in inp.items()}
+    outs = {}
+    for pick in ("0", "1", None):
+        if pick is None:
+            monkeypatch.delenv("CLIK_QP_TAIL_PICK")
+        else:
+            monkeypatch.setenv("CLIK_QP_TAIL_PICK", pick)
+        ctrl = sc.make_controller()
+        ctrl.setup_solver()
+        assert ctrl._skill(0).launch_info(7)["regs"] <= 128 < ctrl._skill(0).launch_info(4)["regs"]
+        outs[pick] = [t.clone() for t in ctrl.solve_batch(dev["t"], dev["q"], dev.get("x"), dev["y"])]
+    for a, b, c in zip(outs["0"], outs["1"], outs[None]):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    assert int(outs["0"][1].abs().sum()) == 0
+
+
 def test_non_finite_data_is_reported_not_returned_as_solved():
     """NaN inputs / a zero weight used to come back with status 0 and NaN velocities."""
     torch = _torch()
