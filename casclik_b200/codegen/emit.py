@@ -517,7 +517,7 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
             out.append("  static constexpr bool QP_CRASH_SINGLE = %s;   // one-row-per-pass prediction passes before the iteration" %
                        ("true" if os.environ.get("CLIK_QP_CRASH_SINGLE", "1") == "1" else "false"))
             out.append("  static constexpr int QP_FAST_PASSES = %d;   // prediction passes in the fast launch (the tail continues)" %
-                       int(os.environ.get("CLIK_QP_FAST_PASSES", "4")))
+                       int(os.environ.get("CLIK_QP_FAST_PASSES", "3")))
             out.append("  static constexpr int QP_FLIP_PASSES = %d;   // first passes in which a released variable may go straight to another bound" %
                        int(os.environ.get("CLIK_QP_FLIP_PASSES", "2")))
             out.append("  static constexpr bool QP_EQ_START = %s;" %

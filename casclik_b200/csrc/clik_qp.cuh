@@ -636,7 +636,8 @@ static long long qp_pass_hist[2][64];   // host-harness instrumentation (tools/q
 #endif
 template <class S, int MAXP = CRASH_PASSES, bool SINGLE = false>
 __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*in: guess, out*/,
-                                            unsigned* lo, double (&xout)[S::QN], bool* still_changing = nullptr) {
+                                            unsigned* lo, double (&xout)[S::QN], bool* still_changing = nullptr,
+                                            const int passes_before = 0 /* passes an earlier launch spent on this set */) {
   constexpr int NX = S::QN, MD = S::QMD, MU = S::QMU, MD1 = MD > 0 ? MD : 1;
   bool eq[MD1];
   double s2[NX], yv[MD1];
@@ -757,7 +758,7 @@ __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*
     // (profiles/r2_qp_pass_stats.txt).  Only a guess changes: every set is still certified by a pass that
     // leaves it unchanged.  Later passes release to "free" (a two-bound flip-flop cannot form).
     double xt[NX];
-    const bool flip = !SINGLE && pass < S::QP_FLIP_PASSES;
+    const bool flip = !SINGLE && passes_before + pass < S::QP_FLIP_PASSES;
 #pragma unroll
     for (int j = 0; j < NX; ++j) xt[j] = (flip && fr[j] != 0 && nf[j] == 0) ? xc[j] - gs[j] : xc[j];
 #pragma unroll
@@ -943,7 +944,8 @@ __device__ __forceinline__ void qp_instance(long long ld, long long i, const dou
     } else {
       if (S::QP_CRASH) {
         bool cycling = false;
-        ok = parked ? crash_guess<S, REST>(d, &wu, &wl, xs, &cycling) : crash_guess<S>(d, &wu, &wl, xs, &cycling);
+        ok = parked ? crash_guess<S, REST>(d, &wu, &wl, xs, &cycling, S::QP_FAST_PASSES)   // same pass sequence as QP_FULL
+                    : crash_guess<S>(d, &wu, &wl, xs, &cycling);
         if (!ok && cycling && S::QP_CRASH_SINGLE) {
 #ifdef CLIK_QP_STATS
           ++qp_stats[1];
