@@ -120,7 +120,7 @@ def _launch_info(ctrl, is_qp):
     info = {"plain": sk.launch_info(0)}
     try:
         info["tma"] = sk.launch_info(2)
-        info["used"] = "tma" if os.environ.get("CLIK_TMA", "0") == "1" else "plain"
+        info["used"] = "tma" if sk.staging() else "plain"
     except Exception:
         info["used"] = "plain"
     return info
@@ -235,6 +235,18 @@ def _launches_per_step(meta, is_qp):
     return 2 if (meta.get("pinv_split") and os.environ.get("CLIK_PINV_SPLIT", "1") != "0") else 1
 
 
+def _use_staging(args, meta, is_qp, counts):
+    """The staged persistent kernel pays where HBM is the nearer roof and another stream covers its ragged last
+    wave (profiles/r2_ab12.txt): roofs compared with this pool's measured peaks
+    (6.55 TB/s copy bandwidth, 33.8 TFLOP/s DFMA), executed fp64 instructions from ncu when known."""
+    if is_qp or not meta.get("pinv_staged_kernel") or args.staged == "off":
+        return False
+    if args.staged == "on":
+        return True
+    f64_inst = counts.get("fp64_inst_per_instance") or meta["pinv_flops_mode0"] / 2.0
+    return args.streams > 1 and meta["pinv_bytes_per_step"] / 6.55e12 > 2.0 * f64_inst / 33.8e12
+
+
 def _overlap_note(level, streams=1):
     note = {0: "0: plain stream order on each stream",
             1: "1: plain stream order between the steps of a stream (the two launches of a two-launch step overlap)",
@@ -245,6 +257,15 @@ def _overlap_note(level, streams=1):
         note += "; the K independent batches alternate over %d CUDA streams (forked from / joined into the " \
                 "timed stream), so the drain of one step overlaps the ramp of the next" % streams
     return note + "; `stream_ordered` is the same K steps on one stream, one kernel after the other"
+
+
+def _kernel_note(staged, is_qp):
+    if is_qp:
+        return "clik_qp_fast_kernel + clik_qp_tail_kernel (capped variant for batches with more tail tiles than resident CTAs)"
+    if staged:
+        return ("clik_pinv_tma_kernel: persistent balanced grid, inputs staged into shared memory by bulk async copies "
+                "(cp.async.bulk + mbarrier) two tiles ahead; `stream_ordered` is the plain clik_pinv_kernel")
+    return "clik_pinv_kernel: one CTA per 128 instances"
 
 
 def _bytes_per_set(meta, is_qp, B):
@@ -349,7 +370,12 @@ def time_device_resident(torch, dist, ctrl, scenario, B, steps, warm, rank, worl
     ms_plain = None
     if (overlap >= 2 or side) and plain_too:
         keep, side[:] = list(side), []
+        staged = bool(getattr(ctrl, "_staging", False))
+        if staged:
+            ctrl.set_input_staging(False)       # a single-stream caller's default: the plain kernel
         ms_plain, _ = timed(min(overlap, 1))
+        if staged:
+            ctrl.set_input_staging(True)
         side[:] = keep
     ms, graphed = timed(overlap)
     return ms, n_sets, graphed, step, ms_plain
@@ -360,9 +386,12 @@ def rooflines(meta, is_qp, B, sec_per_step, hbm_peak, hbm_src, fp64_peak, counts
     (ncu, profiles/r2_ncu_counts.json) when there is one, else from the emitter's algorithmic flops
     (pinv mode 0 only).  The bound is the roof the kernel sits closer to."""
     bytes_step = meta["qp_bytes_per_step"] if is_qp else meta["pinv_bytes_per_step"]
+    # DRAM bytes per launch from ncu (profiles/r2_ncu_counts.json): measured over a RANGE of launches on
+    # distinct buffers when there is such a capture (the outputs of a launch leave L2 after it has ended, so a
+    # per-kernel capture misses most of the writes), else the per-kernel figure
     traffic = None
     if counts.get("batch") == B and counts.get("dram_bytes") is not None:
-        traffic = counts["dram_bytes"]
+        traffic = counts.get("dram_bytes_range_per_launch", counts["dram_bytes"])
     ach = bytes_step * B / sec_per_step / 1e9
     hbm = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
            "traffic": traffic, "peak_source": hbm_src, "algorithmic_bytes_per_step": bytes_step}
@@ -405,6 +434,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--streams", type=int, default=int(os.environ.get("CLIK_BENCH_STREAMS", "2")),
                     help="CUDA streams the K independent batches of the device-resident loop alternate over")
+    ap.add_argument("--staged", default=os.environ.get("CLIK_BENCH_STAGED", "auto"), choices=["auto", "on", "off"],
+                    help="pinv skills: TMA-staged persistent kernel (clik_skill_set_staging); auto = HBM-leaning "
+                         "skills when the batches alternate over several streams")
     ap.add_argument("--overlap", type=int, default=int(os.environ.get("CLIK_PDL", "1")), choices=[0, 1, 2],
                     help="clik_skill_set_overlap level of the device-resident loop (2: independent steps overlap)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -454,6 +486,9 @@ def main():
         c.setup_problem_functions()
         c.setup_solver()
         qp = sc.controller == "qp"
+        staged = _use_staging(args, c.kernel_meta, qp, counts_all.get(name, {}))
+        if staged:
+            c.set_input_staging(True)
         if mode == "strong":
             lo, hi = sharding.shard_range(batch, rank, world)
             Bs = hi - lo
@@ -469,6 +504,7 @@ def main():
         out = {"config": cfg, "workload": sc.description, "value": val, "unit": UNIT,
                "ms_per_step": ms_tot / k, "steps": k, "batch_per_gpu": Bs, "global_batch": total,
                "scaling": mode, "sets_rotated": n_sets, "overlap": _overlap_note(args.overlap, args.streams), "streams": args.streams,
+               "kernel": _kernel_note(staged, qp),
                "gpu_launches": k * _launches_per_step(c.kernel_meta, qp)}
         if ms_plain is not None:
             out["stream_ordered"] = {"value": total * k / (ms_plain * 1e-3), "ms_per_step": ms_plain / k}
@@ -492,6 +528,9 @@ def main():
     ctrl.setup_solver()
     meta = ctrl.kernel_meta
     is_qp = scenario.controller == "qp"
+    staged = _use_staging(args, meta, is_qp, counts_all.get(scenario.name, {}))
+    if staged:
+        ctrl.set_input_staging(True)
     B = args.batch
     # every rank owns an independent shard (weak scaling: B instances per GPU); no collective
     # on the data path — instances are independent
@@ -569,6 +608,7 @@ def main():
                        "launch_mode": ("%d step-kernel launches replayed from one CUDA graph" % args.steps
                                        if graphed else "direct launches"),
                        "overlap": _overlap_note(args.overlap, args.streams), "streams": args.streams,
+                       "kernel": _kernel_note(staged, is_qp),
                        "host_affinity": ("rank 0 bound to its GPU's NUMA node: %d of %d CPUs" % (len(numa[1]), len(numa[0]))
                                          if numa else "unbound"),
                        "l2": "rotating %d resident input + output sets (%d MB of algorithmic traffic in total) "

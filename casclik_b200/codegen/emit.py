@@ -603,14 +603,24 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
             out.append("  clik::pdl_wait();   // reads the mode[] the fast pass wrote")
             out.append("  clik::pinv_group_step<Skill>(N, ld, t, t_stride, q, x, y, qdot, xdot, mode, from_mode, only_pending);")
             out.append("}")
-        if os.environ.get("CLIK_TMA", "0") == "1":
-            # opt-in TMA-staged persistent variant (measured slower than the plain kernel)
+        # TMA-staged persistent variant: slower than the plain kernel when launches run
+        # one after the other, faster for HBM-leaning skills when batches alternate over two streams.  Emitted for
+        # small single-launch skills, used on request (clik_skill_set_staging); CLIK_TMA=1 emits and uses it, 0 never.
+        tma_env = os.environ.get("CLIK_TMA")
+        emit_tma = tma_env == "1" or (tma_env is None and not meta.get("pinv_split")
+                                      and 0 < meta.get("pinv_staged_rows", 0) <= 16 and pinv.m <= 8)
+        meta["pinv_staged_kernel"] = bool(emit_tma)
+        if emit_tma:
+            out.append("#ifndef CLIK_NO_TMA_KERNEL   // (the host test harness cannot compile the mbarrier / bulk-copy PTX)")
             out.append('extern "C" __global__ void %s clik_pinv_tma_kernel(' % bounds)
             out.append("    long long N, long long ld, const double* t, int t_stride, const double* q, const double* x,")
             out.append("    const double* y, double* qdot, double* xdot, int* mode) {")
+            out.append("  clik::pdl_launch_dependents();")
             out.append("  clik::pinv_step_tma<Skill, %d, %d>(N, ld, t, t_stride, q, x, y, qdot, xdot, mode);"
                        % (block_threads, int(os.environ.get("CLIK_STAGES", "2"))))
+            out.append("  clik::pdl_wait();")
             out.append("}")
+            out.append("#endif")
     if qp is not None:
         qmin = int(os.environ.get("CLIK_QP_MINBLOCKS", "0"))
         qbounds = "__launch_bounds__(%d%s)" % (block_threads, (", %d" % qmin) if qmin else "")
@@ -669,7 +679,7 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
     out.append('extern "C" __global__ void clik_sizes_kernel(int* o) {')
     flags = 0
     if pinv is not None:
-        flags |= 2 | (1 if os.environ.get("CLIK_TMA", "0") == "1" else 0)
+        flags |= 2 | (1 if meta.get("pinv_staged_kernel") else 0)
         flags |= (32 if meta.get("pinv_group") else 0) | (64 if meta.get("pinv_split") else 0)
     if qp is not None:
         flags |= (4 if qp_rollout else 0) | (16 if meta.get("qp_split") else 0)

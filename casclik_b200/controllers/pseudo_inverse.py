@@ -177,7 +177,24 @@ class PseudoInverseController(BaseController):
                                                         n_slack=self.skill_spec.n_slack_var, device=dev)
             if getattr(self, "_overlap", None) is not None:
                 self._compiled[dev].set_overlap(self._overlap)
+            if getattr(self, "_staging", None):
+                self._compiled[dev].set_staging(True)
         return self._compiled[dev]
+
+    def set_input_staging(self, on):
+        """Device-resident batches through the TMA-staged persistent kernel (inputs brought into shared memory
+        by bulk async copies two tiles ahead of the arithmetic; include/clik.h clik_skill_set_staging).  Same
+        bits; faster for HBM-leaning skills when independent batches alternate over two CUDA streams, slightly
+        slower on a single stream.  Raises if the skill was compiled without the staged kernel
+        (`kernel_meta["pinv_staged_kernel"]`)."""
+        if on and not self.kernel_meta.get("pinv_staged_kernel"):
+            raise runtime.ClikError("this skill has no staged kernel (two-launch step or too many rows)")
+        self._staging = bool(on)
+        if isinstance(self._compiled, dict):
+            for sk in self._compiled.values():
+                sk.set_staging(self._staging)
+        elif self._compiled is not None:
+            self._compiled.set_staging(self._staging)
 
     def set_overlap(self, level):
         """How successive solve_batch launches on one CUDA stream may overlap (include/clik.h,

@@ -96,7 +96,7 @@ struct clik_skill {
   bool pinv_group_all = false;  // CLIK_PINV_GROUP=1: whole batches through the sub-warp mapping (A/B measurements)
   int n_static = 1;           // statically compiled modes: where the group pass resumes the search
   ReadMask pinv_reads, qp_reads;
-  bool use_tma = false;  // opt-in (CLIK_TMA=1): measured slower than the plain kernel, see DESIGN.md
+  bool use_tma = false;  // clik_skill_set_staging / CLIK_TMA=1: the TMA-staged persistent pinv kernel (device-resident batches)
   // programmatic dependent launch (clik_skill_set_overlap / CLIK_PDL): 0 = plain stream order,
   // 1 = the second launch of a two-launch step is scheduled while the first drains (it waits for the first
   // to complete before it reads), 2 = also the first launch of a step, i.e. successive steps on one stream
@@ -463,6 +463,15 @@ clik_status clik_skill_set_overlap(clik_skill* s, int32_t level) {
 
 int32_t clik_skill_get_overlap(const clik_skill* s) { return s ? s->overlap : -1; }
 
+clik_status clik_skill_set_staging(clik_skill* s, int32_t on) {
+  if (!s) return fail(CLIK_ERR_INVALID, "skill is NULL");
+  if (on && !s->pinv_tma.kernel) return fail(CLIK_ERR_INVALID, "skill was built without the staged pinv kernel");
+  s->use_tma = on != 0;
+  return CLIK_OK;
+}
+
+int32_t clik_skill_get_staging(const clik_skill* s) { return s ? (s->use_tma && s->pinv_tma.kernel ? 1 : 0) : -1; }
+
 void clik_skill_free(clik_skill* s) {
   if (!s) return;
   DeviceGuard guard(s->desc.device);
@@ -496,7 +505,7 @@ namespace {
 // which order copies and kernels on their own streams, never more than 1)
 clik_status pinv_step_impl(const clik_skill* s, int64_t N, int64_t ld, const double* t, int32_t t_stride,
                            const double* q, const double* x, const double* y, double* qdot,
-                           double* xdot, int32_t* mode, void* stream, int level) {
+                           double* xdot, int32_t* mode, void* stream, int level, bool staged_ok = true) {
   clik_status st = check_common(s, N, t, q, x, y);
   if (st != CLIK_OK || N == 0) return st;
   if (ld < N) return fail(CLIK_ERR_INVALID, "row stride ld (%lld) < N (%lld)", (long long)ld, (long long)N);
@@ -508,7 +517,7 @@ clik_status pinv_step_impl(const clik_skill* s, int64_t N, int64_t ld, const dou
   int ts = t_stride ? 1 : 0;
   void* args[] = {&n, &l, &t, &ts, &q, &x, &y, &qdot, &xdot, &mode};
   // bulk async copies need 16-byte aligned row segments: even stride and aligned bases
-  const bool tma_ok = s->use_tma && s->pinv_tma.kernel && (ld % 2 == 0) && aligned16(t) && aligned16(q) &&
+  const bool tma_ok = staged_ok && s->use_tma && s->pinv_tma.kernel && (ld % 2 == 0) && aligned16(t) && aligned16(q) &&
                       aligned16(x) && aligned16(y);
   const int64_t tiles = (N + clik::PINV_TAIL_TILE - 1) / clik::PINV_TAIL_TILE;
   const bool within = level >= 1, across = level >= 2;
@@ -526,8 +535,14 @@ clik_status pinv_step_impl(const clik_skill* s, int64_t N, int64_t ld, const dou
     void* gargs[] = {&n, &l, &t, &ts, &q, &x, &y, &qdot, &xdot, &mode, &from, &pending_only};
     CK(launch(s->pinv_group, (unsigned)std::min<int64_t>(tiles, 1 << 20), gargs, (cudaStream_t)stream, within));
   } else if (tma_ok) {
-    CK(cudaLaunchKernel((const void*)s->pinv_tma.kernel, dim3(balanced_grid(s->pinv_tma, N)),
-                        dim3(s->pinv_tma.block), args, 0, (cudaStream_t)stream));
+    // CLIK_TMA_TILES=T: one CTA per T tiles (hardware CTA scheduling, T tiles staged ahead) instead of the
+    // balanced persistent grid
+    int tiles_per_cta = 0;
+    if (const char* e = getenv("CLIK_TMA_TILES")) tiles_per_cta = atoi(e);
+    const int64_t ntiles = (N + s->pinv_tma.block - 1) / s->pinv_tma.block;
+    const unsigned tgrid = tiles_per_cta > 0 ? (unsigned)std::max<int64_t>(1, (ntiles + tiles_per_cta - 1) / tiles_per_cta)
+                                             : (unsigned)balanced_grid(s->pinv_tma, N);
+    CK(launch(s->pinv_tma, tgrid, args, (cudaStream_t)stream, across));
   } else {
     CK(launch(s->pinv, grid_for(s->pinv, N), args, (cudaStream_t)stream, across));
   }
@@ -692,7 +707,8 @@ clik_status pinv_host_range(clik_skill* s, int64_t N, int64_t lo, int64_t cnt, c
       auto off = [lo](const void* p) { return p ? (const double*)p + lo : nullptr; };
       zs = pinv_step_impl(s, cnt, N, t_stride ? off(dt) : (const double*)dt, t_stride, off(dq), off(dx),
                           off(dy), (double*)off(dqd), (double*)off(dxd),
-                          dm ? (int32_t*)dm + lo : nullptr, s->scratch.stream[0], std::min(s->overlap, 1));
+                          dm ? (int32_t*)dm + lo : nullptr, s->scratch.stream[0], std::min(s->overlap, 1),
+                          /*staged_ok=*/false);   // the inputs are mapped host memory
       if (zs != CLIK_OK) return zs;
       CK(cudaStreamSynchronize(s->scratch.stream[0]));
       return CLIK_OK;

@@ -35,6 +35,7 @@ EXPORTS = (
     "clik_pinv_step_host", "clik_qp_step_host", "clik_skill_launch_info",
     "clik_pinv_step_ld", "clik_qp_step_ld", "clik_pinv_step_host_multi", "clik_qp_step_host_multi",
     "clik_pinv_solve_one", "clik_qp_solve_one", "clik_skill_set_overlap", "clik_skill_get_overlap",
+    "clik_skill_set_staging", "clik_skill_get_staging",
     "clik_measure_fp64_peak", "clik_flush_l2", "clik_device_count", "clik_abi_version",
     "clik_last_error",
 )
@@ -104,6 +105,10 @@ def load_library():
     lib.clik_skill_set_overlap.argtypes = [vp, i32]
     lib.clik_skill_get_overlap.restype = i32
     lib.clik_skill_get_overlap.argtypes = [vp]
+    lib.clik_skill_set_staging.restype = i32
+    lib.clik_skill_set_staging.argtypes = [vp, i32]
+    lib.clik_skill_get_staging.restype = i32
+    lib.clik_skill_get_staging.argtypes = [vp]
     lib.clik_measure_fp64_peak.restype = i32
     lib.clik_measure_fp64_peak.argtypes = [i32, i32, _c_double_p]
     lib.clik_flush_l2.restype = i32
@@ -239,6 +244,13 @@ class CompiledSkill(object):
 
     def overlap(self):
         return int(self._lib.clik_skill_get_overlap(self.handle))
+
+    def set_staging(self, on):
+        """TMA-staged persistent pinv kernel for device-resident batches (include/clik.h clik_skill_set_staging)."""
+        check(self._lib.clik_skill_set_staging(self.handle, 1 if on else 0))
+
+    def staging(self):
+        return int(self._lib.clik_skill_get_staging(self.handle)) == 1
 
     def launch_info(self, which=0):
         g, b, r, l = (ctypes.c_int32() for _ in range(4))

@@ -208,6 +208,17 @@ clik_status clik_qp_step_host_multi(const clik_skill* const* skills, int32_t n_s
 clik_status clik_skill_set_overlap(clik_skill* skill, int32_t level);
 int32_t clik_skill_get_overlap(const clik_skill* skill);
 
+/* Input staging of clik_pinv_step* on device-resident batches: on = the TMA-staged persistent kernel
+ * (one CTA per resident slot walks tiles of 128 instances; the input rows the skill reads are brought into
+ * shared memory by bulk async copies that complete on an mbarrier, two tiles ahead of the arithmetic), off
+ * (default) = one CTA per 128 instances loading its own inputs.  Same results to the bit.  Staging pays for
+ * HBM-leaning skills when batches alternate over two streams (+3 % on the tracking skill) and costs 1-3 % when
+ * launches run one after the other; it needs 16-byte aligned rows (even ld, aligned bases), otherwise the call
+ * silently uses the plain kernel.  CLIK_ERR_INVALID if the image has no staged kernel (skills with a
+ * two-launch step, more than 16 input rows or more than 8 task rows). */
+clik_status clik_skill_set_staging(clik_skill* skill, int32_t on);
+int32_t clik_skill_get_staging(const clik_skill* skill);
+
 /* Launch geometry chosen at load time (for reporting). */
 clik_status clik_skill_launch_info(const clik_skill* skill, int32_t which /*0 pinv, 1 qp, 2 pinv TMA-staged, 3 qp fast pass, 4 qp tail pass, 5 pinv fast pass, 6 pinv group pass, 7 qp tail pass capped to 4 CTAs/SM (large batches)*/,
                                    int32_t* grid, int32_t* block, int32_t* regs_per_thread,

@@ -452,3 +452,42 @@ def test_overlapped_launches_give_the_bits_of_plain_stream_order(name, env, monk
         assert sums == ref_sums
     if is_qp:
         assert np.all(ref[0][1] == runtime.QP_SOLVED)
+
+
+def test_staged_kernel_on_two_streams_gives_the_bits_of_the_plain_kernel():
+    """clik_skill_set_staging: the TMA-staged persistent kernel is compiled into every small single-launch pinv
+    skill and switched on per handle; batches alternating over two streams, even and odd sizes (odd: rows are
+    not 16-byte aligned, the call falls back to the plain kernel), results equal the plain kernel's bits."""
+    torch = _torch()
+    sc = scenarios.get("ur5_track")
+    ctrl = sc.make_controller()
+    ctrl.setup_solver()
+    assert ctrl.kernel_meta["pinv_staged_kernel"] and not ctrl._skill(0).staging()
+    side = torch.cuda.Stream()
+    for N in (262_144 + 2, 77_777):
+        ins = []
+        for s in range(4):
+            inp = sc.sample(N, seed=70 + s)
+            ins.append(tuple(_up(inp.get(k)) for k in ("t", "q", "x", "y")))
+        res = {}
+        for staged in (False, True):
+            ctrl.set_input_staging(staged)
+            assert ctrl._skill(0).staging() == staged
+            outs = [None] * 4
+            side.wait_stream(torch.cuda.current_stream())
+            for s in range(4):
+                if s % 2:
+                    with torch.cuda.stream(side):
+                        outs[s] = ctrl.solve_batch(*ins[s])
+                else:
+                    outs[s] = ctrl.solve_batch(*ins[s])
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            res[staged] = [(o[0].cpu().numpy(), o[2].cpu().numpy()) for o in outs]
+        for (va, ma), (vb, mb) in zip(res[False], res[True]):
+            assert np.array_equal(va, vb) and np.array_equal(ma, mb)
+    iiwa = scenarios.get("iiwa_multitask_stress").make_controller()     # 19 input rows: no staged kernel
+    iiwa.setup_problem_functions(load=False)
+    assert not iiwa.kernel_meta["pinv_staged_kernel"]
+    with pytest.raises(runtime.ClikError):
+        iiwa.set_input_staging(True)

@@ -50,6 +50,7 @@ static inline unsigned __activemask() { return 1u; }
 static inline int __any_sync(unsigned, int p) { return p; }
 static inline int __all_sync(unsigned, int p) { return p; }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
+#define CLIK_NO_TMA_KERNEL 1
 #define CLIK_GROUP 1   // sub-warp mapping with groups of one lane: same code path, one host "thread"
 static inline void __syncthreads() {}
 static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }

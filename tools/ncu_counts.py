@@ -49,6 +49,18 @@ def main():
             data = json.load(f)
     for arg in sys.argv[1:]:
         spec, path = arg.split(":", 1)
+        if spec.startswith("range="):
+            # range=<scenario>=<launches in the range>:<csv of tools/ncu_range_traffic.py under --replay-mode range>:
+            # DRAM bytes of K consecutive launches on K distinct buffer sets, write-back included
+            _, name, k = spec.split("=")
+            rows = parse(path)
+            rd = sum(r.get("dram__bytes_read.sum", 0.0) for r in rows)
+            wr = sum(r.get("dram__bytes_write.sum", 0.0) for r in rows)
+            data.setdefault(name, {})["dram_bytes_range_per_launch"] = (rd + wr) / int(k)
+            data[name]["dram_range"] = {"launches": int(k), "read": rd, "write": wr,
+                                        "source": "ncu --replay-mode range, %s" % os.path.basename(path)}
+            print(name, "range of %s launches: %.1f MB per launch" % (k, (rd + wr) / int(k) / 1e6))
+            continue
         name, batch = spec.split("=")
         batch = int(batch)
         launches = [l for l in parse(path) if l["kernel"].startswith("clik_") and "sizes" not in l["kernel"]
@@ -78,12 +90,14 @@ def main():
             kernels[k] = rec
             for key in tot:
                 tot[key] += rec[key]
+        keep = {k: v for k, v in data.get(name, {}).items() if k.startswith("dram_range") or k == "dram_bytes_range_per_launch"}
         data[name] = {"batch": batch, "dram_bytes": tot["dram_bytes_read"] + tot["dram_bytes_write"],
                       "dram_bytes_read": tot["dram_bytes_read"], "dram_bytes_write": tot["dram_bytes_write"],
                       "fp64_inst_per_instance": 32.0 * tot["fp64_warp_inst"] / batch,
                       "inst_per_instance": 32.0 * tot["warp_inst"] / batch,
                       "ncu_time_us_per_step": tot["time_us"], "kernels": kernels,
                       "source": "ncu --metrics pass, %s" % os.path.basename(path)}
+        data[name].update(keep)
         print(name, json.dumps({k: v for k, v in data[name].items() if k != "kernels"}))
     with open(OUT, "w") as f:
         json.dump(data, f, indent=1, sort_keys=True)
