@@ -522,6 +522,16 @@ def emit_skill(pinv=None, qp=None, label="skill", block_threads=None, min_blocks
                        int(os.environ.get("CLIK_QP_FLIP_PASSES", "2")))
             out.append("  static constexpr bool QP_EQ_START = %s;" %
                        ("true" if os.environ.get("CLIK_QP_EQ_START", "0") == "1" else "false"))
+            # structural zeros of the dense rows (slack columns of other rows, joints a task does not depend on):
+            # skipped at compile time in the prediction passes, like jnz() in the pinv algebra
+            admask = [sum((1 << j) for j in range(qp.nx) if qp.A[r][j] is not dag.ZERO) for r in qp.dense_rows] or [0]
+            if os.environ.get("CLIK_QP_ADNZ", "1") != "1":
+                admask = [(1 << qp.nx) - 1 for _ in admask]
+            meta["qp_dense_nnz"] = sum(bin(v).count("1") for v in admask)
+            out.append("  __host__ __device__ static constexpr bool ad_nz(int a, int j) {")
+            out.append("    constexpr unsigned m[%d] = {%s};" % (len(admask), ", ".join("0x%xu" % v for v in admask)))
+            out.append("    return (m[a] >> j) & 1u;")
+            out.append("  }")
             out.append(_switch("dense_row", qp.dense_rows or [0]))
             out.append(_switch("unit_row", [r for r, _, _ in qp.unit_rows] or [0]))
             out.append(_switch("unit_col", [c for _, c, _ in qp.unit_rows] or [0]))

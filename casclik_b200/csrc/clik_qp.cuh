@@ -687,13 +687,13 @@ __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*
     for (int a = 0; a < MD; ++a) {
       double rhs = (da[a] < 0) ? D.lbd[a] : D.ubd[a];
 #pragma unroll
-      for (int j = 0; j < NX; ++j) rhs = fma(-D.Ad[a * NX + j], xf[j], rhs);
+      for (int j = 0; j < NX; ++j) { if (S::ad_nz(a, j)) rhs = fma(-D.Ad[a * NX + j], xf[j], rhs); }
       yv[a] = (da[a] != 0) ? rhs : 0.0;
 #pragma unroll
       for (int b = 0; b <= a; ++b) {
         double g = 0.0;
 #pragma unroll
-        for (int j = 0; j < NX; ++j) g = fma(D.Ad[a * NX + j] * w[j], D.Ad[b * NX + j], g);
+        for (int j = 0; j < NX; ++j) { if (S::ad_nz(a, j) && S::ad_nz(b, j)) g = fma(D.Ad[a * NX + j] * w[j], D.Ad[b * NX + j], g); }
         G[a * MD1 + b] = (da[a] != 0 && da[b] != 0) ? g : ((a == b) ? 1.0 : 0.0);
       }
     }
@@ -736,7 +736,7 @@ __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*
     for (int j = 0; j < NX; ++j) {
       double tj = 0.0;
 #pragma unroll
-      for (int a = 0; a < MD; ++a) tj = fma(D.Ad[a * NX + j], yv[a], tj);
+      for (int a = 0; a < MD; ++a) { if (S::ad_nz(a, j)) tj = fma(D.Ad[a * NX + j], yv[a], tj); }
       const double xfree = s2[j] * tj;
       xc[j] = (fr[j] == 0) ? xfree : xf[j];
       gs[j] = xf[j] - xfree;
@@ -785,7 +785,7 @@ __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*
     for (int a = 0; a < MD; ++a) {
       double r = 0.0;
 #pragma unroll
-      for (int j = 0; j < NX; ++j) r = fma(D.Ad[a * NX + j], xc[j], r);
+      for (int j = 0; j < NX; ++j) { if (S::ad_nz(a, j)) r = fma(D.Ad[a * NX + j], xc[j], r); }
       const double bnd = (da[a] < 0) ? D.lbd[a] : D.ubd[a];
       held_ok = held_ok && (da[a] == 0 || fabs(r - bnd) <= 1e-11 * (1.0 + fabs(bnd)));
       int na = (da[a] > 0 && yv[a] <= 0.0) ? 1 : ((da[a] < 0 && yv[a] >= 0.0) ? -1 : 0);

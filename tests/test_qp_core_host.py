@@ -150,6 +150,7 @@ SHIM_S = SHIM.split('#include "%s"')[0] + r'''
 struct S {
   static constexpr int QN = 6, QMD = 2, QMU = 7, QM = 9;
   static constexpr int QP_FLIP_PASSES = 2;
+  static constexpr bool ad_nz(int, int) { return true; }
   static constexpr int dense_row(int a) { return a == 0 ? 1 : 4; }
   static constexpr int unit_row(int i) { constexpr int t[7] = {0, 2, 3, 5, 6, 7, 8}; return t[i]; }
   static constexpr int unit_col(int i) { constexpr int t[7] = {0, 1, 2, 0, 3, 5, 1}; return t[i]; }
@@ -408,6 +409,7 @@ SHIM_G = SHIM.split('#include "%s"')[0] + r'''
 struct S {
   static constexpr int QN = %(qn)d, QMD = %(md)d, QMU = %(mu)d, QM = %(qm)d;
   static constexpr int QP_FLIP_PASSES = 2;
+  static constexpr bool ad_nz(int, int) { return true; }
   static constexpr int dense_row(int a) { constexpr int t[%(md1)d] = {%(dense)s}; return t[a]; }
   static constexpr int unit_row(int i) { constexpr int t[%(mu1)d] = {%(urow)s}; return t[i]; }
   static constexpr int unit_col(int i) { constexpr int t[%(mu1)d] = {%(ucol)s}; return t[i]; }
