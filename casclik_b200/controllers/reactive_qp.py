@@ -182,6 +182,15 @@ class ReactiveQPController(BaseController):
                 source, meta, cubin, path = src3, meta3, cubin3, path3
                 meta["register_cap"] = ("fast kernel launch_bounds(128, 3): natural allocation was %d registers, "
                                         "%d B local under the cap" % (regs, local3))
+                # one more step (4 CTAs/SM, 128 registers) when even that leaves a small frame: UR5 9x15 232 B,
+                # +2-5 %; Moe-2016 496 B, -4 % (profiles/r2_ab14.txt)
+                src4, meta4 = emit_skill(qp=prog, label=self.skill_spec.label, qp_fast_min_blocks=4)
+                cubin4, path4 = build.compile_cubin(src4, tag="qp_" + self.skill_spec.label)
+                local4 = build.kernel_stack_bytes(path4, "clik_qp_fast_kernel")
+                if local4 is not None and local4 <= 256:
+                    source, meta, cubin, path = src4, meta4, cubin4, path4
+                    meta["register_cap"] = ("fast kernel launch_bounds(128, 4): natural allocation was %d registers, "
+                                            "%d B local under the cap" % (regs, local4))
         self.kernel_source, self.kernel_meta, self.cubin_path = source, meta, path
         self._nxv, self._ny, self._qn, self._qm = prog.n_virt, prog.n_in, prog.nx, prog.m
         self.row_labels = prog.labels
