@@ -73,3 +73,31 @@ def test_product_tree_never_touches_the_oracle_or_the_reference():
                         re.search(r"^\s*(import|from)\s+casadi\b", text, re.M):
                     bad.append(os.path.join(dirpath, fn))
     assert bad == []
+
+
+def test_overlap_and_staging_switches_validate_without_a_device():
+    """clik_skill_set_overlap / clik_skill_set_staging: argument errors need no GPU, and the controller-level
+    switches are remembered until a skill handle exists."""
+    from casclik_b200 import scenarios
+    lib = runtime.load_library()
+    assert lib.clik_skill_set_overlap(None, 1) == 1 and b"NULL" in lib.clik_last_error()
+    assert lib.clik_skill_set_staging(None, 1) == 1
+    assert lib.clik_skill_get_overlap(None) == -1 and lib.clik_skill_get_staging(None) == -1
+    ctrl = scenarios.get("ur5_track").make_controller()
+    ctrl.setup_problem_functions(load=False)
+    assert ctrl.kernel_meta["pinv_staged_kernel"] is True
+    ctrl.set_overlap(2)
+    ctrl.set_input_staging(True)
+    assert ctrl._overlap == 2 and ctrl._staging is True
+    with pytest.raises(ValueError):
+        ctrl.set_overlap(3)
+    big = scenarios.get("iiwa_multitask_stress").make_controller()
+    big.setup_problem_functions(load=False)
+    assert big.kernel_meta["pinv_staged_kernel"] is False       # 19 input rows, 16 task rows
+    with pytest.raises(runtime.ClikError):
+        big.set_input_staging(True)
+    qp = scenarios.get("ur5_qp").make_controller()
+    qp.setup_problem_functions(load=False)
+    qp.set_overlap(0)
+    assert qp._overlap == 0
+    assert qp.kernel_meta["qp_tail_cap"] == 4 and qp.kernel_meta["qp_dense_nnz"] == 17
