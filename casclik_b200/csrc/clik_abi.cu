@@ -155,10 +155,17 @@ clik_status setup_kernel(clik_skill* s, const char* name, KernelInfo* k) {
   return CLIK_OK;
 }
 
+// Zero-copy host calls (kernel running on mapped host memory) may cap the grid: CTAs per SM of a grid-stride
+// launch (0 = no cap).  Set around the launch by the host entry points.
+thread_local int g_ctas_per_sm_cap = 0;
+thread_local int g_sm_count = 0;
+
 int grid_for(const KernelInfo& k, int64_t N) {
   const int64_t per_cta = (int64_t)k.block * k.unroll;
   int64_t need = (N + per_cta - 1) / per_cta;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(need, k.grid));
+  int64_t cap = k.grid;
+  if (g_ctas_per_sm_cap > 0 && g_sm_count > 0) cap = std::min<int64_t>(cap, (int64_t)g_ctas_per_sm_cap * g_sm_count);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(need, cap));
 }
 
 // Persistent grid for the TMA-staged kernel: the fewest waves that cover all tiles, then the
@@ -284,6 +291,27 @@ bool device_alias(const void* host, const void** dev) {
   *dev = a.devicePointer;
   return true;
 }
+
+// CLIK_ZC_STAGED=1: let the zero-copy path use the staged kernel too (bulk async copies straight from the
+// mapped host arrays) when the skill has staging switched on
+bool zero_copy_staged() {
+  static bool v = [] { const char* e = getenv("CLIK_ZC_STAGED"); return e != nullptr && atoi(e) != 0; }();
+  return v;
+}
+
+// Grid of a kernel that runs directly on mapped host memory: a grid-stride launch of 2 CTAs per SM instead of
+// one CTA per 128 instances.  With ~1200 CTAs resident the 8 input rows are read at ~1200 scattered places at
+// once; with 296 the requests the host sees are far more sequential: 6.2e8 -> 7.0e8 steps/s end to end for the
+// tracking skill, 94 % of what two concurrent memcpys reach on this box (profiles/r2_ab18.txt).
+// CLIK_ZC_CTAS_PER_SM overrides (0 = no cap).
+int zero_copy_ctas_per_sm() {
+  static int v = [] { const char* e = getenv("CLIK_ZC_CTAS_PER_SM"); return e ? atoi(e) : 2; }();
+  return v;
+}
+struct GridCapScope {
+  GridCapScope(int cap, int sms) { g_ctas_per_sm_cap = cap; g_sm_count = sms; }
+  ~GridCapScope() { g_ctas_per_sm_cap = 0; }
+};
 
 bool zero_copy_enabled() {
   static bool v = [] { const char* e = getenv("CLIK_ZERO_COPY"); return e == nullptr || atoi(e) != 0; }();
@@ -705,10 +733,11 @@ clik_status pinv_host_range(clik_skill* s, int64_t N, int64_t lo, int64_t cnt, c
       clik_status zs = ensure_scratch(s, 0, 256);
       if (zs != CLIK_OK) return zs;
       auto off = [lo](const void* p) { return p ? (const double*)p + lo : nullptr; };
+      GridCapScope cap(zero_copy_ctas_per_sm(), s->sm_count);
       zs = pinv_step_impl(s, cnt, N, t_stride ? off(dt) : (const double*)dt, t_stride, off(dq), off(dx),
                           off(dy), (double*)off(dqd), (double*)off(dxd),
                           dm ? (int32_t*)dm + lo : nullptr, s->scratch.stream[0], std::min(s->overlap, 1),
-                          /*staged_ok=*/false);   // the inputs are mapped host memory
+                          /*staged_ok=*/zero_copy_staged());   // the inputs are mapped host memory
       if (zs != CLIK_OK) return zs;
       CK(cudaStreamSynchronize(s->scratch.stream[0]));
       return CLIK_OK;
@@ -753,6 +782,7 @@ clik_status qp_host_range(clik_skill* s, int64_t N, int64_t lo, int64_t cnt, con
       clik_status zs = ensure_scratch(s, 0, 256);
       if (zs != CLIK_OK) return zs;
       auto off = [lo](const void* p) { return p ? (const double*)p + lo : nullptr; };
+      GridCapScope cap(zero_copy_ctas_per_sm(), s->sm_count);
       zs = qp_step_impl(s, cnt, N, t_stride ? off(dt) : (const double*)dt, t_stride, off(dq), off(dx), off(dy),
                         off(dx0), da0 ? (const uint32_t*)da0 + lo : nullptr, (double*)off(dsol),
                         dst ? (int32_t*)dst + lo : nullptr, dact ? (uint32_t*)dact + lo : nullptr, max_iter,
