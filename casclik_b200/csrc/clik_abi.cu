@@ -617,7 +617,7 @@ namespace {
 clik_status qp_step_impl(const clik_skill* s, int64_t N, int64_t ld, const double* t, int32_t t_stride,
                          const double* q, const double* x, const double* y, const double* x0,
                          const uint32_t* active0, double* sol, int32_t* status, uint32_t* active,
-                         int32_t max_iter, void* stream, int level) {
+                         int32_t max_iter, void* stream, int level, bool split_ok = true) {
   clik_status st = check_common(s, N, t, q, x, y);
   if (st != CLIK_OK || N == 0) return st;
   if (ld < N) return fail(CLIK_ERR_INVALID, "row stride ld (%lld) < N (%lld)", (long long)ld, (long long)N);
@@ -629,7 +629,7 @@ clik_status qp_step_impl(const clik_skill* s, int64_t N, int64_t ld, const doubl
   int mi = max_iter > 0 ? max_iter : 10 * (s->desc.qp_n + s->desc.qp_m);
   void* args[] = {&n, &l, &t, &ts, &q, &x, &y, &x0, &active0, &sol, &status, &active, &mi};
   const bool within = level >= 1, across = level >= 2;
-  if (s->qp_fast.kernel && s->qp_tail.kernel && s->qp_split && status != nullptr) {
+  if (split_ok && s->qp_fast.kernel && s->qp_tail.kernel && s->qp_split && status != nullptr) {
     // two launches: the working-set prediction for every instance (no Goldfarb-Idnani code in that
     // kernel: ~160 registers instead of 255 + spills), then the full solver for the few instances the
     // prediction could not certify; they are handed over through status[] (transient value 3).
@@ -786,7 +786,10 @@ clik_status qp_host_range(clik_skill* s, int64_t N, int64_t lo, int64_t cnt, con
       zs = qp_step_impl(s, cnt, N, t_stride ? off(dt) : (const double*)dt, t_stride, off(dq), off(dx), off(dy),
                         off(dx0), da0 ? (const uint32_t*)da0 + lo : nullptr, (double*)off(dsol),
                         dst ? (int32_t*)dst + lo : nullptr, dact ? (uint32_t*)dact + lo : nullptr, max_iter,
-                        s->scratch.stream[0], std::min(s->overlap, 1));
+                        s->scratch.stream[0], std::min(s->overlap, 1),
+                        // one kernel: a tail pass would scan status[] and re-read the inputs of the pending
+                        // instances over PCIe (1.7e8 vs 4.4-4.8e8 steps/s for the UR5 problem, profiles/r2_ab19.txt)
+                        /*split_ok=*/false);
       if (zs != CLIK_OK) return zs;
       CK(cudaStreamSynchronize(s->scratch.stream[0]));
       return CLIK_OK;
