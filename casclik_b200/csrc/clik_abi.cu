@@ -533,7 +533,8 @@ namespace {
 // which order copies and kernels on their own streams, never more than 1)
 clik_status pinv_step_impl(const clik_skill* s, int64_t N, int64_t ld, const double* t, int32_t t_stride,
                            const double* q, const double* x, const double* y, double* qdot,
-                           double* xdot, int32_t* mode, void* stream, int level, bool staged_ok = true) {
+                           double* xdot, int32_t* mode, void* stream, int level, bool staged_ok = true,
+                           bool split_ok = true) {
   clik_status st = check_common(s, N, t, q, x, y);
   if (st != CLIK_OK || N == 0) return st;
   if (ld < N) return fail(CLIK_ERR_INVALID, "row stride ld (%lld) < N (%lld)", (long long)ld, (long long)N);
@@ -554,7 +555,7 @@ clik_status pinv_step_impl(const clik_skill* s, int64_t N, int64_t ld, const dou
     int from = 0, pending_only = 0;
     void* gargs[] = {&n, &l, &t, &ts, &q, &x, &y, &qdot, &xdot, &mode, &from, &pending_only};
     CK(launch(s->pinv_group, (unsigned)std::min<int64_t>(tiles, 1 << 20), gargs, (cudaStream_t)stream, across));
-  } else if (s->pinv_split && s->pinv_fast.kernel && s->pinv_group.kernel && mode != nullptr) {
+  } else if (split_ok && s->pinv_split && s->pinv_fast.kernel && s->pinv_group.kernel && mode != nullptr) {
     // two launches: statically compiled modes for every instance (thread mapping, registers), then the
     // run-time tail of the activation map for the instances they all rejected (sub-warp mapping);
     // handed over through mode[] (transient value PINV_PENDING)
@@ -737,7 +738,8 @@ clik_status pinv_host_range(clik_skill* s, int64_t N, int64_t lo, int64_t cnt, c
       zs = pinv_step_impl(s, cnt, N, t_stride ? off(dt) : (const double*)dt, t_stride, off(dq), off(dx),
                           off(dy), (double*)off(dqd), (double*)off(dxd),
                           dm ? (int32_t*)dm + lo : nullptr, s->scratch.stream[0], std::min(s->overlap, 1),
-                          /*staged_ok=*/zero_copy_staged());   // the inputs are mapped host memory
+                          /*staged_ok=*/zero_copy_staged(),    // the inputs are mapped host memory:
+                          /*split_ok=*/false);                 // no hand-over through mode[] over PCIe either
       if (zs != CLIK_OK) return zs;
       CK(cudaStreamSynchronize(s->scratch.stream[0]));
       return CLIK_OK;
