@@ -646,6 +646,11 @@ __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*
   // the caller's guess (the previous step's working set in a rollout, or nothing) seeds the iteration:
   // an unchanged set is confirmed by the first pass
   const unsigned gu = *up, gl = *lo;
+  // (the shortcut below for released variables is for cold predictions only: from a warm start — the
+  // previous step's set in a rollout — a variable whose multiplier changes sign simply becomes free, and
+  // testing it at its coordinate-wise optimum sends it to the opposite bound far too often: QP rollout
+  // 6.9e9 -> 5.3e9 controller-steps/s with the shortcut applied to warm starts)
+  const bool cold = (gu | gl) == 0u;
 #pragma unroll
   for (int j = 0; j < NX; ++j) { s2[j] = D.s[j] * D.s[j]; fr[j] = 0; }
 #pragma unroll
@@ -756,9 +761,10 @@ __device__ __forceinline__ bool crash_guess(const QpSData<S>& D, unsigned* up /*
     // in this pass instead of going through "free" first.  For the UR5 problem this takes the mean number
     // of passes from 3.6 to 2.8 and the share of instances final after 3 passes from 40 % to 91 %
     // (profiles/r2_qp_pass_stats.txt).  Only a guess changes: every set is still certified by a pass that
-    // leaves it unchanged.  Later passes release to "free" (a two-bound flip-flop cannot form).
+    // leaves it unchanged.  Later passes release to "free" (a two-bound flip-flop cannot form), and so do
+    // all passes of a warm-started prediction.
     double xt[NX];
-    const bool flip = !SINGLE && passes_before + pass < S::QP_FLIP_PASSES;
+    const bool flip = !SINGLE && cold && passes_before + pass < S::QP_FLIP_PASSES;
 #pragma unroll
     for (int j = 0; j < NX; ++j) xt[j] = (flip && fr[j] != 0 && nf[j] == 0) ? xc[j] - gs[j] : xc[j];
 #pragma unroll
