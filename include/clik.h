@@ -156,7 +156,10 @@ clik_status clik_qp_dense(int32_t device, int64_t N, int32_t nx, int32_t m, cons
 /* Host-buffer variants (same argument meaning, HOST pointers, synchronous).  Pageable memory goes
  * through a chunked H2D / kernel / D2H pipeline on internal streams; if every buffer is page-locked
  * (cudaHostAlloc / cudaHostRegister, torch pin_memory()) the kernel runs directly on the mapped
- * host memory instead (CLIK_ZERO_COPY=0 disables this). */
+ * host memory instead (CLIK_ZERO_COPY=0 disables this): one kernel per call (no fast + tail hand-over
+ * through host memory), launched as a grid-stride grid of 2 CTAs per SM so that the reads the host sees
+ * stay nearly sequential (CLIK_ZC_CTAS_PER_SM overrides, 0 = one CTA per 128 instances).  Results are
+ * bit-identical to the device-pointer entry points on every path. */
 clik_status clik_pinv_step_host(const clik_skill* skill, int64_t N, const double* t,
                                 int32_t t_stride, const double* q, const double* x,
                                 const double* y, double* qdot, double* xdot, int32_t* mode);
